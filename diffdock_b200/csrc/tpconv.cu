@@ -1,0 +1,463 @@
+// Fused tensor-product graph convolution for sm_100a (B200).
+//
+// One warp owns a run of 32 consecutive edges (edges are CSR-sorted by destination).  For every edge it
+//   1. gathers the source node's irreps row (L2-resident) into shared memory,
+//   2. evaluates the real spherical harmonics of the edge vector in registers,
+//   3. folds Clebsch-Gordan blocks x Y into small per-path matrices M and forms z[u,k] = sum_i x[u,i] M[i,k],
+//   4. streams the edge's weight row (the dominant HBM stream, 11-28 KB per edge) through a private ring of shared
+//      memory stages filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) and contracts it with z,
+//      each weight being used for 1..5 FMAs and never re-read,
+//   5. keeps the running sum of a destination row in a lane-distributed shared accumulator and flushes it with
+//      fp32 reductions (RED.ADD) when the destination changes.
+// Everything that depends on the irreps (paths, CG entries, tile -> lane mapping, TMA chunking) comes from the table
+// blob built by diffdock_b200/tp_table.py, so one binary serves every (ns, nv, sh_lmax, ...) configuration.
+//
+// Reference semantics: models/tensor_layers.py:125-231 (tp_scatter_simple / tp_scatter_multigroup).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/diffdock_b200.h"
+
+namespace {
+
+constexpr int WARP = 32;
+constexpr int HDR = 32;
+constexpr int ERUN = 32;          // edges per work unit (one lane holds one edge's indices/geometry)
+constexpr int MAX_XREG = 8;       // register prefetch of the next source row covers D_in <= 256
+constexpr uint32_t MAGIC = 0x44423230u;
+
+struct KParams {
+  const float* x; long long x_stride;
+  const int* esrc; const int* edst;
+  const float* geo; const float* ew;
+  const float* w; long long w_stride;
+  long long n_edges;
+  float* sum; float* cnt;
+  const int* iblob; const float* fblob;
+  int n_ints, n_terms;
+  int stages, warps;
+  int warp_floats;    // per-warp scratch size in floats
+  int stage_floats;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+template <int DOUT>
+__device__ __forceinline__ void contract_tile(const float* __restrict__ wp, const float* __restrict__ zp, int rows,
+                                              int r, int R, int rs, float* __restrict__ acc_slot) {
+  float acc[DOUT];
+#pragma unroll
+  for (int k = 0; k < DOUT; ++k) acc[k] = 0.f;
+  const int wstep = R * rs, zstep = R * DOUT;
+  wp += r * rs;
+  zp += r * DOUT;
+#pragma unroll 4
+  for (int u = r; u < rows; u += R) {
+    const float wv = *wp;
+#pragma unroll
+    for (int k = 0; k < DOUT; ++k) acc[k] = fmaf(wv, zp[k], acc[k]);
+    wp += wstep;
+    zp += zstep;
+  }
+#pragma unroll
+  for (int k = 0; k < DOUT; ++k) acc_slot[k * WARP] += acc[k];
+}
+
+__global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- CTA-shared: table copy ---------------------------------------------------------------------------------
+  int* tb = reinterpret_cast<int*>(smem_raw);
+  for (int i = threadIdx.x; i < p.n_ints; i += blockDim.x) tb[i] = p.iblob[i];
+  float* tval = reinterpret_cast<float*>(tb + ((p.n_ints + 3) & ~3));
+  for (int i = threadIdx.x; i < p.n_terms; i += blockDim.x) tval[i] = p.fblob[i];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tval + ((p.n_terms + 3) & ~3));
+  float* warp_base = reinterpret_cast<float*>(bars + ((p.warps * p.stages + 1) & ~1));
+  warp_base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(warp_base) + 127) & ~uintptr_t(127));
+  if (lane == 0)
+    for (int s = 0; s < p.stages; ++s) mbar_init(&bars[warp * p.stages + s], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int n_paths = tb[1], n_chunks = tb[3], n_ment = tb[4];
+  const int D_in = tb[6], D_sh = tb[7], D_out = tb[8], lmax = tb[9];
+  const int z_total = tb[10], m_total = tb[11], n_acc = tb[12];
+  const int* paths = tb + tb[15];
+  const int* tiles = tb + tb[16];
+  const int* chunks = tb + tb[17];
+  const int* ment = tb + tb[18];
+  const int* terms_y = tb + tb[19];
+  const int* outmap = tb + tb[20];
+
+  // ---- per-warp scratch ---------------------------------------------------------------------------------------
+  float* wsm = warp_base + (size_t)warp * p.warp_floats;
+  float* stage_base = wsm;                                     // stages * stage_floats
+  float* xs = stage_base + (size_t)p.stages * p.stage_floats;  // D_in
+  float* ys = xs + ((D_in + 3) & ~3);                          // D_sh
+  float* ms = ys + ((D_sh + 3) & ~3);                          // m_total
+  float* zs = ms + ((m_total + 3) & ~3);                       // z_total
+  float* racc = zs + ((z_total + 3) & ~3);                     // n_acc * 32
+  uint64_t* mybar = bars + warp * p.stages;
+  for (int i = lane; i < n_acc * WARP; i += WARP) racc[i] = 0.f;
+
+  const long long E = p.n_edges;
+  const long long n_units = (E + ERUN - 1) / ERUN;
+  const long long TW = (long long)gridDim.x * p.warps;
+  const long long gw = (long long)blockIdx.x * p.warps + warp;
+  const uint64_t policy = policy_evict_first();
+
+  // ---- producer cursor (all lanes track it, lane 0 issues) -----------------------------------------------------
+  long long p_unit = gw, p_e = gw * ERUN;
+  int p_c = 0, p_stage = 0;
+  auto issue_next = [&]() {
+    if (p_unit < n_units) {
+      if (lane == 0) {
+        const int* ch = chunks + 4 * p_c;
+        const uint32_t bytes = (uint32_t)ch[3] * 4u;
+        mbar_expect_tx(&mybar[p_stage], bytes);
+        bulk_g2s(stage_base + (size_t)p_stage * p.stage_floats, p.w + p_e * p.w_stride + ch[2], bytes,
+                 &mybar[p_stage], policy);
+      }
+      if (++p_c == n_chunks) {
+        p_c = 0;
+        long long uend = (p_unit + 1) * ERUN;
+        if (uend > E) uend = E;
+        if (++p_e >= uend) {
+          p_unit += TW;
+          p_e = p_unit * ERUN;
+        }
+      }
+      p_stage = (p_stage + 1 == p.stages) ? 0 : p_stage + 1;
+    }
+  };
+  for (int s = 0; s < p.stages; ++s) issue_next();
+
+  int c_stage = 0;
+  uint32_t c_par = 0;
+  const int nxr = (D_in + WARP - 1) / WARP;
+
+  for (long long unit = gw; unit < n_units; unit += TW) {
+    const long long e0 = unit * ERUN;
+    const int ne = (int)((E - e0) < ERUN ? (E - e0) : ERUN);
+    // one edge per lane: indices + geometry
+    int l_src = 0, l_dst = -1;
+    float l_vx = 0.f, l_vy = 0.f, l_vz = 0.f, l_ew = 1.f;
+    if (lane < ne) {
+      l_src = p.esrc[e0 + lane];
+      l_dst = p.edst[e0 + lane];
+      if (lmax >= 0) {
+        const float* g = p.geo + 3 * (e0 + lane);
+        l_vx = g[0]; l_vy = g[1]; l_vz = g[2];
+      }
+      if (p.ew) l_ew = p.ew[e0 + lane];
+    }
+    int cur_row = -1, row_edges = 0;
+    float xr[MAX_XREG];
+    {  // source row of the first edge
+      const int s0 = __shfl_sync(0xffffffffu, l_src, 0);
+      const float* xrow = p.x + (long long)s0 * p.x_stride;
+#pragma unroll
+      for (int j = 0; j < MAX_XREG; ++j) xr[j] = (j < nxr && lane + WARP * j < D_in) ? __ldg(xrow + lane + WARP * j) : 0.f;
+    }
+    for (int i = 0; i < ne; ++i) {
+      const int dst = __shfl_sync(0xffffffffu, l_dst, i);
+      const int src = __shfl_sync(0xffffffffu, l_src, i);
+      const float ewt = __shfl_sync(0xffffffffu, l_ew, i);
+      if (dst != cur_row) {
+        if (cur_row >= 0) {
+          __syncwarp();
+          float* srow = p.sum + (long long)cur_row * D_out;
+          for (int o = lane; o < D_out; o += WARP) {
+            const int* om = outmap + 3 * o;
+            float v = 0.f;
+            for (int r = 0; r < om[2]; ++r) v += racc[om[0] + r * om[1]];
+            atomicAdd(srow + o, v);
+          }
+          if (p.cnt && lane == 0) atomicAdd(p.cnt + cur_row, (float)row_edges);
+          __syncwarp();
+          for (int j = lane; j < n_acc * WARP; j += WARP) racc[j] = 0.f;
+        }
+        cur_row = dst;
+        row_edges = 0;
+      }
+      ++row_edges;
+      // ---- stage x row (prefetched registers -> smem); large rows fall back to direct loads -------------------
+#pragma unroll
+      for (int j = 0; j < MAX_XREG; ++j)
+        if (j < nxr && lane + WARP * j < D_in) xs[lane + WARP * j] = xr[j];
+      if (nxr > MAX_XREG) {
+        const float* xrow = p.x + (long long)src * p.x_stride;
+        for (int j = MAX_XREG * WARP + lane; j < D_in; j += WARP) xs[j] = __ldg(xrow + j);
+      }
+      // ---- spherical harmonics -----------------------------------------------------------------------------------
+      if (lmax >= 0) {
+        float vx = __shfl_sync(0xffffffffu, l_vx, i), vy = __shfl_sync(0xffffffffu, l_vy, i),
+              vz = __shfl_sync(0xffffffffu, l_vz, i);
+        const float nrm = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
+        vx /= nrm; vy /= nrm; vz /= nrm;
+        if (lane == 0) {
+          ys[0] = 1.f;
+          if (lmax >= 1) {
+            const float s3 = 1.7320508075688772f;
+            ys[1] = s3 * vx; ys[2] = s3 * vy; ys[3] = s3 * vz;
+          }
+          if (lmax >= 2) {
+            const float s5 = 2.23606797749979f, s15 = 3.872983346207417f;
+            ys[4] = s15 * vx * vz;
+            ys[5] = s15 * vx * vy;
+            ys[6] = s5 * (vy * vy - 0.5f * (vx * vx + vz * vz));
+            ys[7] = s15 * vy * vz;
+            ys[8] = 0.5f * s15 * (vz * vz - vx * vx);
+          }
+        }
+      } else {
+        const float* g = p.geo + (e0 + i) * (long long)D_sh;
+        for (int j = lane; j < D_sh; j += WARP) ys[j] = __ldg(g + j);
+      }
+      __syncwarp();
+      // ---- M[i,k] = edge_weight * sum_j (coef*C[i,j,k]) * Y[j] --------------------------------------------------
+      for (int m = lane; m < n_ment; m += WARP) {
+        const int* me = ment + 3 * m;
+        float a = 0.f;
+        for (int q = me[1]; q < me[1] + me[2]; ++q) a = fmaf(tval[q], ys[terms_y[q]], a);
+        ms[me[0]] = a * ewt;
+      }
+      __syncwarp();
+      // ---- z[u,k] = sum_i x[u,i] * M[i,k] -----------------------------------------------------------------------
+      for (int q = 0; q < n_paths; ++q) {
+        const int* pa = paths + 6 * q;
+        const int in_off = pa[0], mul_in = pa[1], din = pa[2], dout = pa[3];
+        const float* mp = ms + pa[5];
+        float* zp = zs + pa[4];
+        const int n = mul_in * dout;
+        for (int idx = lane; idx < n; idx += WARP) {
+          const int u = idx / dout, k = idx - u * dout;
+          const float* xp = xs + in_off + u * din;
+          float a = 0.f;
+          for (int ii = 0; ii < din; ++ii) a = fmaf(xp[ii], mp[ii * dout + k], a);
+          zp[idx] = a;
+        }
+      }
+      __syncwarp();
+      // ---- prefetch the next edge's source row while the weights are contracted --------------------------------
+      if (i + 1 < ne) {
+        const int s1 = __shfl_sync(0xffffffffu, l_src, i + 1);
+        const float* xrow = p.x + (long long)s1 * p.x_stride;
+#pragma unroll
+        for (int j = 0; j < MAX_XREG; ++j)
+          xr[j] = (j < nxr && lane + WARP * j < D_in) ? __ldg(xrow + lane + WARP * j) : 0.f;
+      }
+      // ---- weight contraction, chunk by chunk ------------------------------------------------------------------
+      for (int c = 0; c < n_chunks; ++c) {
+        const int* ch = chunks + 4 * c;
+        while (!mbar_try_wait(&mybar[c_stage], c_par)) {}
+        const float* st = stage_base + (size_t)c_stage * p.stage_floats;
+        for (int t = ch[0]; t < ch[1]; ++t) {
+          const int* ti = tiles + 8 * t;
+          const int width = ti[5], R = ti[6];
+          const int r = lane / width, wl = lane - r * width;
+          if (r < R) {
+            const float* wp = st + ti[0] + wl;
+            const float* zp = zs + ti[3];
+            float* as = racc + ti[7] + lane;
+            switch (ti[4]) {
+              case 1: contract_tile<1>(wp, zp, ti[2], r, R, ti[1], as); break;
+              case 3: contract_tile<3>(wp, zp, ti[2], r, R, ti[1], as); break;
+              case 5: contract_tile<5>(wp, zp, ti[2], r, R, ti[1], as); break;
+              case 7: contract_tile<7>(wp, zp, ti[2], r, R, ti[1], as); break;
+              default: contract_tile<9>(wp, zp, ti[2], r, R, ti[1], as); break;
+            }
+          }
+        }
+        __syncwarp();
+        issue_next();   // refill the stage that was just drained
+        if (++c_stage == p.stages) { c_stage = 0; c_par ^= 1u; }
+      }
+    }
+    // flush the last row of this run
+    if (cur_row >= 0) {
+      __syncwarp();
+      float* srow = p.sum + (long long)cur_row * D_out;
+      for (int o = lane; o < D_out; o += WARP) {
+        const int* om = outmap + 3 * o;
+        float v = 0.f;
+        for (int r = 0; r < om[2]; ++r) v += racc[om[0] + r * om[1]];
+        atomicAdd(srow + o, v);
+      }
+      if (p.cnt && lane == 0) atomicAdd(p.cnt + cur_row, (float)row_edges);
+      __syncwarp();
+      for (int j = lane; j < n_acc * WARP; j += WARP) racc[j] = 0.f;
+    }
+  }
+}
+
+__global__ void tpconv_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ cnt, long long n_rows,
+                                       int d_out, int mean, const float* __restrict__ bn_scale,
+                                       const float* __restrict__ bn_shift, const float* __restrict__ residual,
+                                       long long res_stride, int res_dim, float* __restrict__ out) {
+  const long long total = n_rows * d_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / d_out;
+    const int c = (int)(i - n * d_out);
+    float v = sum[i];
+    if (mean) v = v / fmaxf(cnt[n], 1.1920928955078125e-07f);   // torch.finfo(float32).eps, tensor_layers.py:228
+    if (bn_scale) v = fmaf(v, bn_scale[c], bn_shift[c]);
+    if (residual && c < res_dim) v += residual[n * res_stride + c];
+    out[i] = v;
+  }
+}
+
+}  // namespace
+
+struct ddb200_tp_table {
+  int* d_iblob;
+  float* d_fblob;
+  int hdr[HDR];
+  int n_ints, n_terms;
+  int warps, stages, warp_floats, smem_bytes;
+};
+
+static int plan_smem(ddb200_tp_table* t) {
+  const int* h = t->hdr;
+  const int D_in = h[6], D_sh = h[7], m_total = h[11], z_total = h[10], n_acc = h[12], stage_floats = h[14];
+  auto al4 = [](int v) { return (v + 3) & ~3; };
+  const int fixed = al4(D_in) + al4(D_sh) + al4(m_total) + al4(z_total) + n_acc * WARP;
+  int dev = 0, max_smem = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || max_smem <= 0)
+    max_smem = 227 * 1024;
+  const int shared_bytes = (al4(t->n_ints) + al4(t->n_terms)) * 4 + 256;
+  // prefer 8 warps x 2 stages; fall back to fewer warps, never fewer than 2 stages
+  for (int warps = 8; warps >= 1; --warps) {
+    for (int stages = 3; stages >= 2; --stages) {
+      if (warps == 8 && stages == 3) continue;  // 8x3 never fits next to the scratch for the full-width layer
+      const int wf = (stages * stage_floats + fixed + 31) & ~31;
+      const long long need = (long long)shared_bytes + 8LL * (warps * stages + 2) + 128 + 4LL * wf * warps;
+      if (need <= max_smem) {
+        t->warps = warps; t->stages = stages; t->warp_floats = wf; t->smem_bytes = (int)need;
+        return 0;
+      }
+    }
+  }
+  return DDB200_ESMEM;
+}
+
+extern "C" {
+
+const char* ddb200_version(void) { return "diffdock_b200 0.1.0 sm_100a"; }
+
+int ddb200_tp_table_create(const int32_t* ib, int n_ints, const float* fb, int n_floats, ddb200_tp_table** out) {
+  if (!ib || !fb || !out || n_ints < HDR) return DDB200_EINVAL;
+  if ((uint32_t)ib[0] != MAGIC || ib[21] != n_ints || ib[5] > n_floats) return DDB200_ETABLE;
+  if (ib[13] % 4 || ib[14] % 4 || ib[1] <= 0 || ib[3] <= 0) return DDB200_ETABLE;
+  ddb200_tp_table* t = (ddb200_tp_table*)calloc(1, sizeof(ddb200_tp_table));
+  if (!t) return DDB200_EINVAL;
+  memcpy(t->hdr, ib, sizeof(int) * HDR);
+  t->n_ints = n_ints;
+  t->n_terms = ib[5];
+  int rc = plan_smem(t);
+  if (rc) { free(t); return rc; }
+  cudaError_t e = cudaMalloc(&t->d_iblob, sizeof(int) * n_ints);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_fblob, sizeof(float) * (n_floats > 0 ? n_floats : 1));
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_iblob, ib, sizeof(int) * n_ints, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_fblob, fb, sizeof(float) * n_floats, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tpconv_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) { ddb200_tp_table_destroy(t); return (int)e; }
+  *out = t;
+  return 0;
+}
+
+void ddb200_tp_table_destroy(ddb200_tp_table* t) {
+  if (!t) return;
+  if (t->d_iblob) cudaFree(t->d_iblob);
+  if (t->d_fblob) cudaFree(t->d_fblob);
+  free(t);
+}
+
+int ddb200_tp_table_info(const ddb200_tp_table* t, int what) {
+  if (!t) return DDB200_EINVAL;
+  switch (what) {
+    case 0: return t->hdr[6];
+    case 1: return t->hdr[7];
+    case 2: return t->hdr[8];
+    case 3: return t->hdr[13];
+    case 4: return t->hdr[9];
+    case 5: return t->smem_bytes;
+    case 6: return t->warps;
+    case 7: return t->stages;
+    default: return DDB200_EINVAL;
+  }
+}
+
+int ddb200_tpconv_accumulate(const ddb200_tp_table* t, const float* x, int64_t x_stride, const int32_t* edge_src,
+                             const int32_t* edge_dst, const float* geo, const float* edge_weight, const float* w,
+                             int64_t w_stride, int64_t n_edges, float* sum, float* cnt, void* stream) {
+  if (!t || !x || !edge_src || !edge_dst || !geo || !w || !sum || n_edges < 0) return DDB200_EINVAL;
+  if (n_edges == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(w) & 15) || (w_stride & 3) || w_stride < t->hdr[13] || x_stride < t->hdr[6])
+    return DDB200_EINVAL;
+  KParams p;
+  p.x = x; p.x_stride = x_stride; p.esrc = edge_src; p.edst = edge_dst; p.geo = geo; p.ew = edge_weight;
+  p.w = w; p.w_stride = w_stride; p.n_edges = n_edges; p.sum = sum; p.cnt = cnt;
+  p.iblob = t->d_iblob; p.fblob = t->d_fblob; p.n_ints = t->n_ints; p.n_terms = t->n_terms;
+  p.stages = t->stages; p.warps = t->warps; p.warp_floats = t->warp_floats; p.stage_floats = t->hdr[14];
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long units = (n_edges + ERUN - 1) / ERUN;
+  long long ctas = (units + t->warps - 1) / t->warps;
+  if (ctas > sms) ctas = sms;   // persistent: one CTA per SM, warps stride over the edge runs
+  tpconv_accumulate_kernel<<<(unsigned)ctas, t->warps * WARP, t->smem_bytes, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int ddb200_tpconv_finalize(const float* sum, const float* cnt, int64_t n_rows, int d_out, int mean,
+                           const float* bn_scale, const float* bn_shift, const float* residual, int64_t res_stride,
+                           int res_dim, float* out, void* stream) {
+  if (!sum || !out || n_rows < 0 || d_out <= 0 || (mean && !cnt) || ((bn_scale == nullptr) != (bn_shift == nullptr)))
+    return DDB200_EINVAL;
+  if (n_rows == 0) return 0;
+  const long long total = n_rows * (long long)d_out;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tpconv_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sum, cnt, n_rows, d_out, mean, bn_scale,
+                                                                            bn_shift, residual, res_stride, res_dim, out);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

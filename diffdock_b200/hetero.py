@@ -1,0 +1,170 @@
+"""Duck-typed stand-in for the torch_geometric ``HeteroData`` / ``Batch`` objects the reference passes
+to ``model(data)`` (utils/sampling.py:80,116).  torch_geometric is not installed in this image; the
+score model only relies on the attribute contract listed in SURVEY.md section 8(b), which this class
+provides.  A real PyG ``HeteroDataBatch`` satisfies the same contract and is accepted unchanged.
+
+Edge-store keys follow PyG: a 2-tuple ``('ligand', 'ligand')`` resolves to the single edge type with
+those endpoints (datasets/process_mols.py:202,294-295).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List
+
+import torch
+
+
+def _map(v, fn):
+    if torch.is_tensor(v):
+        return fn(v)
+    if isinstance(v, dict):
+        return {k: _map(x, fn) for k, x in v.items()}
+    return v
+
+
+class Store:
+    """Attribute bag for one node or edge type."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def num_nodes(self):
+        for k in ('x', 'pos', 'batch'):
+            if k in self.__dict__:
+                return self.__dict__[k].shape[0]
+        return 0
+
+    @property
+    def num_edges(self):
+        return self.__dict__['edge_index'].shape[1] if 'edge_index' in self.__dict__ else 0
+
+    def keys(self):
+        return list(self.__dict__.keys())
+
+    def __contains__(self, k):
+        return k in self.__dict__
+
+    def _apply(self, fn):
+        for k, v in list(self.__dict__.items()):
+            self.__dict__[k] = _map(v, fn)
+        return self
+
+
+class HeteroGraph:
+    """One complex, or a batch of complexes (``num_graphs`` > 1, with per-node ``batch`` vectors)."""
+
+    def __init__(self):
+        object.__setattr__(self, '_nodes', {})
+        object.__setattr__(self, '_edges', {})
+        object.__setattr__(self, '_globals', {})
+
+    # -- item access --------------------------------------------------------------------------
+    def __getitem__(self, key):
+        if isinstance(key, tuple):
+            key = (key[0], key[-1])
+            if key not in self._edges:
+                self._edges[key] = Store()
+            return self._edges[key]
+        if key in self._globals:
+            return self._globals[key]
+        if key not in self._nodes:
+            self._nodes[key] = Store()
+        return self._nodes[key]
+
+    def __setitem__(self, key, value):
+        self._globals[key] = value
+
+    def __getattr__(self, name):
+        g = object.__getattribute__(self, '_globals')
+        if name in g:
+            return g[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self._globals[name] = value
+
+    def __contains__(self, key):
+        return key in self._globals or key in self._nodes
+
+    @property
+    def node_types(self):
+        return list(self._nodes.keys())
+
+    @property
+    def edge_types(self):
+        return list(self._edges.keys())
+
+    # -- movement / copies --------------------------------------------------------------------
+    def _apply(self, fn):
+        for s in list(self._nodes.values()) + list(self._edges.values()):
+            s._apply(fn)
+        for k, v in list(self._globals.items()):
+            self._globals[k] = _map(v, fn)
+        return self
+
+    def to(self, device, non_blocking=False):
+        return self._apply(lambda t: t.to(device, non_blocking=non_blocking))
+
+    def cpu(self):
+        return self.to('cpu')
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    def __deepcopy__(self, memo):
+        g = HeteroGraph()
+        for k, s in self._nodes.items():
+            g._nodes[k] = Store(**{a: copy.deepcopy(v, memo) for a, v in s.__dict__.items()})
+        for k, s in self._edges.items():
+            g._edges[k] = Store(**{a: copy.deepcopy(v, memo) for a, v in s.__dict__.items()})
+        for a, v in self._globals.items():
+            g._globals[a] = copy.deepcopy(v, memo)
+        return g
+
+
+_LIST_ATTRS = ('mask_rotate', 'name', 'mol')
+
+
+def collate(data_list: List[HeteroGraph]) -> HeteroGraph:
+    """Equivalent of ``torch_geometric.data.Batch.from_data_list`` for the attributes the path uses:
+    node tensors are concatenated, ``edge_index`` is offset by the cumulative node counts of its endpoint
+    types, ``batch`` vectors and ``num_graphs`` are added, non-tensor attributes become lists."""
+    out = HeteroGraph()
+    B = len(data_list)
+    offsets: Dict[str, List[int]] = {}
+    for nt in data_list[0].node_types:
+        counts = [d[nt].num_nodes for d in data_list]
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        offsets[nt] = offs
+        st = out[nt]
+        for attr in data_list[0][nt].keys():
+            vals = [getattr(d[nt], attr) for d in data_list]
+            if attr in _LIST_ATTRS or not torch.is_tensor(vals[0]):
+                setattr(st, attr, vals)
+            else:
+                setattr(st, attr, torch.cat(vals, 0))
+        st.batch = torch.cat([torch.full((c,), i, dtype=torch.long) for i, c in enumerate(counts)])
+        st.ptr = torch.tensor(offs, dtype=torch.long)
+    for et in data_list[0].edge_types:
+        st = out[et]
+        for attr in data_list[0][et].keys():
+            vals = [getattr(d[et], attr) for d in data_list]
+            if attr == 'edge_index':
+                o0, o1 = offsets[et[0]], offsets[et[1]]
+                vals = [v + torch.tensor([[o0[i]], [o1[i]]], dtype=v.dtype) for i, v in enumerate(vals)]
+                st.edge_index = torch.cat(vals, 1)
+            elif torch.is_tensor(vals[0]):
+                setattr(st, attr, torch.cat(vals, 0))
+            else:
+                setattr(st, attr, vals)
+    for k in data_list[0]._globals.keys():
+        vals = [d._globals[k] for d in data_list]
+        if torch.is_tensor(vals[0]):
+            out._globals[k] = torch.cat([v if v.dim() > 0 else v[None] for v in vals], 0)
+        else:
+            out._globals[k] = vals
+    out._globals['num_graphs'] = B
+    return out

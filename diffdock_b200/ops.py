@@ -1,0 +1,90 @@
+"""Tensor-level wrappers over the C ABI (device pointers + current CUDA stream).  CUDA tensors only."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .tp_table import TpTable
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("diffdock_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+class TpHandle:
+    """Device-resident tensor-product table (ddb200_tp_table)."""
+
+    def __init__(self, table: TpTable):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA device required")
+        self.table = table
+        h = C.c_void_p()
+        ib = np.ascontiguousarray(table.iblob, dtype=np.int32)
+        fb = np.ascontiguousarray(table.fblob, dtype=np.float32)
+        rc = _lib.lib().ddb200_tp_table_create(ib.ctypes.data_as(C.c_void_p), len(ib), fb.ctypes.data_as(C.c_void_p),
+                                               len(fb), C.byref(h))
+        _lib.check(rc, 'ddb200_tp_table_create')
+        self._h = h
+
+    def __deepcopy__(self, memo):
+        return TpHandle(self.table)
+
+    def info(self, what):
+        return _lib.lib().ddb200_tp_table_info(self._h, what)
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                _lib.lib().ddb200_tp_table_destroy(self._h)
+        except Exception:
+            pass
+
+
+def tpconv_accumulate(h: TpHandle, x, edge_src, edge_dst, geo, w, sum_buf, cnt_buf=None, edge_weight=None):
+    """sum_buf[edge_dst[e]] += TP(x[edge_src[e]], Y(geo[e]), w[e]) (* edge_weight[e]);  cnt_buf[edge_dst[e]] += 1."""
+    _need_cuda(x, edge_src, edge_dst, geo, w, sum_buf)
+    E = edge_src.shape[0]
+    if E == 0:
+        return
+    t = h.table
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and geo.dtype == torch.float32
+    assert edge_src.dtype == torch.int32 and edge_dst.dtype == torch.int32
+    assert x.stride(1) == 1 and w.stride(1) == 1 and geo.is_contiguous() and sum_buf.is_contiguous()
+    assert edge_src.is_contiguous() and edge_dst.is_contiguous()
+    assert x.shape[1] == t.d_in and w.shape[1] >= t.weight_numel_padded and sum_buf.shape[1] == t.d_out
+    assert geo.shape[0] == E and w.shape[0] == E and geo.shape[1] == (3 if t.sh_lmax >= 0 else t.d_sh)
+    if edge_weight is not None:
+        edge_weight = edge_weight.reshape(-1).contiguous().float()
+        assert edge_weight.shape[0] == E
+    rc = _lib.lib().ddb200_tpconv_accumulate(h._h, _ptr(x), x.stride(0), _ptr(edge_src), _ptr(edge_dst), _ptr(geo),
+                                             _ptr(edge_weight), _ptr(w), w.stride(0), E, _ptr(sum_buf), _ptr(cnt_buf),
+                                             _stream())
+    _lib.check(rc, 'ddb200_tpconv_accumulate')
+
+
+def tpconv_finalize(sum_buf, cnt_buf, mean, bn_scale=None, bn_shift=None, residual=None, out=None):
+    _need_cuda(sum_buf)
+    n, d = sum_buf.shape
+    if out is None:
+        out = torch.empty_like(sum_buf)
+    res_stride = residual.stride(0) if residual is not None else 0
+    res_dim = residual.shape[1] if residual is not None else 0
+    if residual is not None:
+        assert residual.stride(1) == 1 and residual.shape[0] == n and res_dim <= d
+    rc = _lib.lib().ddb200_tpconv_finalize(_ptr(sum_buf), _ptr(cnt_buf), n, d, 1 if mean else 0, _ptr(bn_scale),
+                                           _ptr(bn_shift), _ptr(residual), res_stride, res_dim, _ptr(out), _stream())
+    _lib.check(rc, 'ddb200_tpconv_finalize')
+    return out

@@ -1,0 +1,240 @@
+"""Drop-in for the reference's ``models/tensor_layers.py``: same class name, constructor keywords, ``forward``
+signature and ``state_dict`` keys (``fc.{g}.{0,3}.weight/bias``, ``batch_norm.{weight,bias,running_mean,running_var}``),
+with the convolution executed by the fused sm_100a kernel (csrc/tpconv.cu) instead of
+e3nn + torch_scatter (models/tensor_layers.py:125-231,309-335).
+
+Inference only (eval-mode BatchNorm, dropout = identity); CUDA only - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .irreps import irreps_dim, parse_irreps
+from .tp_table import build_table
+
+ACTIVATIONS = {'relu': nn.ReLU, 'silu': nn.SiLU}
+
+# upper bound on the bytes of per-edge tensor-product weights materialised at once (edges are processed in blocks)
+WEIGHT_BLOCK_BYTES = 6 << 30
+
+
+def get_irrep_seq(ns, nv, use_second_order_repr, reduce_pseudoscalars):
+    """Same four-stage irreps ladder as models/tensor_layers.py:17-32."""
+    tail = f'{nv if reduce_pseudoscalars else ns}x0o'
+    if use_second_order_repr:
+        steps = [f'{ns}x0e', f'{nv}x1o + {nv}x2e', f'{nv}x1e + {nv}x2o', tail]
+    else:
+        steps = [f'{ns}x0e', f'{nv}x1o', f'{nv}x1e', tail]
+    return [' + '.join(steps[:i + 1]) for i in range(4)]
+
+
+def irrep_to_size(irrep):
+    return irreps_dim(parse_irreps(irrep))
+
+
+def FCBlock(in_dim, hidden_dim, out_dim, layers, dropout, activation='relu'):
+    """Radial MLP with the reference's nn.Sequential index layout (models/layers.py:10-17)."""
+    act = ACTIVATIONS[activation]
+    assert layers >= 2
+    mods = [nn.Linear(in_dim, hidden_dim), act(), nn.Dropout(dropout)]
+    for _ in range(layers - 2):
+        mods += [nn.Linear(hidden_dim, hidden_dim), act(), nn.Dropout(dropout)]
+    mods.append(nn.Linear(hidden_dim, out_dim))
+    return nn.Sequential(*mods)
+
+
+class IrrepsBatchNorm(nn.Module):
+    """Parameter container with e3nn.nn.BatchNorm's state_dict layout; eval-mode arithmetic is folded into a
+    per-column (scale, shift) pair consumed by the convolution epilogue (ddb200_tpconv_finalize)."""
+
+    def __init__(self, irreps, eps=1e-5):
+        super().__init__()
+        self.irreps = parse_irreps(irreps)
+        self.eps = eps
+        n_scalar = sum(m for m, l, p in self.irreps if l == 0 and p == 1)
+        n_field = sum(m for m, _, _ in self.irreps)
+        self.register_buffer('running_mean', torch.zeros(n_scalar))
+        self.register_buffer('running_var', torch.ones(n_field))
+        self.weight = nn.Parameter(torch.ones(n_field))
+        self.bias = nn.Parameter(torch.zeros(n_scalar))
+        rep, sc_col, sc_idx, col, f, s = [], [], [], 0, 0, 0
+        for m, l, p in self.irreps:
+            d = 2 * l + 1
+            for u in range(m):
+                rep += [f + u] * d
+                if l == 0 and p == 1:
+                    sc_col.append(col + u)
+                    sc_idx.append(s + u)
+            col += m * d
+            f += m
+            if l == 0 and p == 1:
+                s += m
+        self.register_buffer('_rep', torch.tensor(rep, dtype=torch.long), persistent=False)
+        self.register_buffer('_sc_col', torch.tensor(sc_col, dtype=torch.long), persistent=False)
+        self.register_buffer('_sc_idx', torch.tensor(sc_idx, dtype=torch.long), persistent=False)
+        self._cache = None
+
+    def fold(self):
+        key = (self.weight._version, self.bias._version, self.running_mean._version, self.running_var._version,
+               self.weight.device)
+        if self._cache is None or self._cache[0] != key:
+            with torch.no_grad():
+                s_f = self.weight * (self.running_var + self.eps).pow(-0.5)
+                scale = s_f[self._rep].contiguous().float()
+                shift = torch.zeros_like(scale)
+                if self._sc_col.numel():
+                    shift[self._sc_col] = self.bias[self._sc_idx] - self.running_mean[self._sc_idx] * scale[self._sc_col]
+            self._cache = (key, scale, shift)
+        return self._cache[1], self._cache[2]
+
+
+class _TpSpec(nn.Module):
+    """Stands where the reference keeps ``self.tp`` (weight_numel, irreps); holds the kernel tables."""
+
+    def __init__(self, in_irreps, sh_irreps, out_irreps, kind):
+        super().__init__()
+        self.kind = kind
+        self.in_irreps, self.sh_irreps, self.out_irreps = in_irreps, sh_irreps, out_irreps
+        shs = parse_irreps(sh_irreps)
+        self.vec_capable = shs == [(1, l, (-1) ** l) for l in range(len(shs))] and len(shs) <= 3
+        self.table_sh = build_table(in_irreps, sh_irreps, out_irreps, kind, sh_from_vector=False)
+        self.table_vec = build_table(in_irreps, sh_irreps, out_irreps, kind, sh_from_vector=True) \
+            if self.vec_capable else None
+        self.weight_numel = self.table_sh.weight_numel
+        self._handles = {}
+
+    def handle(self, from_vec):
+        k = bool(from_vec)
+        if k not in self._handles:
+            self._handles[k] = ops.TpHandle(self.table_vec if k else self.table_sh)
+        return self._handles[k]
+
+
+class TensorProductConvLayer(nn.Module):
+    def __init__(self, in_irreps, sh_irreps, out_irreps, n_edge_features, residual=True, batch_norm=True, dropout=0.0,
+                 hidden_features=None, faster=False, edge_groups=1, tp_weights_layers=2, activation='relu',
+                 depthwise=False):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError("depthwise_convolution is outside the hot-path scope (SURVEY.md section 8)")
+        self.in_irreps, self.out_irreps, self.sh_irreps = in_irreps, out_irreps, sh_irreps
+        self.residual, self.edge_groups = residual, edge_groups
+        self.out_size = irrep_to_size(out_irreps) if isinstance(out_irreps, str) else irreps_dim(parse_irreps(out_irreps))
+        self.depthwise = False
+        if hidden_features is None:
+            hidden_features = n_edge_features
+        self.tp = _TpSpec(in_irreps, sh_irreps, out_irreps, 'faster' if faster else 'fctp')
+        if edge_groups == 1:
+            self.fc = FCBlock(n_edge_features, hidden_features, self.tp.weight_numel, tp_weights_layers, dropout, activation)
+        else:
+            self.fc = nn.ModuleList([FCBlock(n_edge_features, hidden_features, self.tp.weight_numel, tp_weights_layers,
+                                             dropout, activation) for _ in range(edge_groups)])
+        self.batch_norm = IrrepsBatchNorm(out_irreps) if batch_norm else None
+        self._wcache = {}
+
+    # -- radial MLP -> per-edge weights in kernel layout ------------------------------------------------------
+    def _last_linear(self, fc, table):
+        """(weight, bias) of the last Linear, permuted/padded to the kernel's weight-row layout if needed."""
+        lin = fc[-1]
+        if table.identity_layout:
+            return lin.weight, lin.bias
+        key = (id(fc), lin.weight._version, lin.bias._version, lin.weight.device)
+        hit = self._wcache.get(id(fc))
+        if hit is None or hit[0] != key:
+            perm = torch.as_tensor(table.w_perm, device=lin.weight.device)
+            ok = perm >= 0
+            W = lin.weight.new_zeros((perm.numel(), lin.weight.shape[1]))
+            b = lin.bias.new_zeros(perm.numel())
+            W[ok], b[ok] = lin.weight.detach()[perm[ok]], lin.bias.detach()[perm[ok]]
+            hit = (key, W, b)
+            self._wcache[id(fc)] = hit
+        return hit[1], hit[2]
+
+    def _edge_weights(self, fc, table, edge_attr):
+        h = edge_attr
+        for m in list(fc)[:-1]:
+            h = m(h)
+        W, b = self._last_linear(fc, table)
+        return F.linear(h, W, b)
+
+    # -- forward -------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0,
+                edge_vec=None, assume_sorted=False):
+        """Reference signature (models/tensor_layers.py:309) plus two optional extensions:
+        ``edge_vec`` [E,3]: evaluate the spherical harmonics in-kernel from the edge vectors (``edge_sh`` is ignored);
+        ``assume_sorted``: every edge group is already sorted by target node ``edge_index[0]``."""
+        if self.training:
+            raise RuntimeError("diffdock_b200 layers are inference-only: call .eval()")
+        if edge_index.shape[1] == 0 and node_attr.shape[0] == 0:
+            raise ValueError("No edges and no nodes")
+        if not node_attr.is_cuda:
+            raise RuntimeError("diffdock_b200.TensorProductConvLayer runs on CUDA tensors only (no CPU fallback)")
+        assert reduce in ('mean', 'sum'), "Only 'mean' and 'sum' are supported for reduce"
+        _dtype = node_attr.dtype
+        x = node_attr.float()
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        n_out = int(out_nodes) if out_nodes else x.shape[0]
+        E = edge_index.shape[1]
+        scale, shift = self.batch_norm.fold() if self.batch_norm is not None else (None, None)
+        if E == 0:   # models/tensor_layers.py:314-315: zeros, no BatchNorm, residual still applies
+            out = torch.zeros((x.shape[0], self.out_size), dtype=torch.float32, device=x.device)
+            if self.residual:
+                out[:, :x.shape[1]] += x
+            return out.to(_dtype)
+
+        if self.edge_groups == 1:
+            assert isinstance(edge_attr, torch.Tensor), "a single edge group takes a tensor edge_attr"
+            groups, fcs = [edge_attr], [self.fc]
+        else:
+            assert isinstance(edge_attr, list), "This function is only for a list of edge groups"
+            groups = edge_attr
+            fcs = list(self.fc) if isinstance(self.fc, nn.ModuleList) else [self.fc] * len(groups)
+        assert sum(g.shape[0] for g in groups) == E, "Sum of edge_attr_groups must be equal to edge_index.shape[1]"
+
+        from_vec = edge_vec is not None and self.tp.vec_capable
+        handle = self.tp.handle(from_vec)
+        table = handle.table
+        geo_all = (edge_vec if from_vec else edge_sh).float()
+        ew_all = edge_weight if torch.is_tensor(edge_weight) else None
+        ew_scalar = 1.0 if torch.is_tensor(edge_weight) else float(edge_weight)
+
+        sum_buf = torch.zeros((n_out, self.out_size), dtype=torch.float32, device=x.device)
+        cnt_buf = torch.zeros((n_out,), dtype=torch.float32, device=x.device)
+        blk = max(1024, WEIGHT_BLOCK_BYTES // (4 * table.weight_numel_padded))
+        s = 0
+        for ea, fc in zip(groups, fcs):
+            e = s + ea.shape[0]
+            if e == s:
+                continue
+            tgt, src = edge_index[0, s:e], edge_index[1, s:e]
+            geo, ew = geo_all[s:e], (ew_all[s:e].reshape(-1) if ew_all is not None else None)
+            if not assume_sorted:
+                tgt, order = torch.sort(tgt, stable=True)
+                src, geo, ea = src[order], geo[order], ea[order]
+                if ew is not None:
+                    ew = ew[order]
+            tgt32, src32 = tgt.to(torch.int32).contiguous(), src.to(torch.int32).contiguous()
+            geo = geo.contiguous()
+            for b0 in range(0, e - s, blk):
+                b1 = min(e - s, b0 + blk)
+                w = self._edge_weights(fc, table, ea[b0:b1].float())
+                if ew_scalar != 1.0:
+                    w = w * ew_scalar
+                ops.tpconv_accumulate(handle, x, src32[b0:b1], tgt32[b0:b1], geo[b0:b1], w, sum_buf, cnt_buf,
+                                      edge_weight=ew[b0:b1] if ew is not None else None)
+                del w
+            s = e
+        res = x if self.residual else None
+        out = ops.tpconv_finalize(sum_buf, cnt_buf, reduce == 'mean', scale, shift, res)
+        return out.to(_dtype)
+
+
+class OldTensorProductConvLayer(nn.Module):
+    def __init__(self, *a, **k):
+        super().__init__()
+        raise NotImplementedError("OldTensorProductConvLayer (confidence model, SURVEY.md row f2) is not built yet")

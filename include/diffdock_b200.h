@@ -1,0 +1,88 @@
+/*
+ * diffdock_b200 - C ABI of the B200-native DiffDock score-model hot path.
+ *
+ * The reference (gcorso/DiffDock @ b4704d9) is pure Python: it has no FFI of its own.  Each entry point below
+ * replaces the op sequence of the cited reference lines; the Python host code in diffdock_b200/ binds them with
+ * ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator); nothing is freed here;
+ *   - every launch goes to the caller-supplied `stream` (cudaStream_t passed as void*), no implicit sync;
+ *   - return value: 0 = ok, otherwise a cudaError_t value or a negative DDB200_E* code; nothing throws;
+ *   - indices are int32 (N, E < 2^31); the Python wrappers convert the reference's int64 indices;
+ *   - floating point is fp32 everywhere (the reference path is fp32, TF32 disabled).
+ */
+#ifndef DIFFDOCK_B200_H
+#define DIFFDOCK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDB200_EINVAL (-1) /* bad argument (alignment, size, null pointer)           */
+#define DDB200_ETABLE (-2) /* malformed tensor-product table blob                    */
+#define DDB200_ESMEM  (-3) /* table needs more shared memory than one SM offers      */
+
+/* library / build information: "diffdock_b200 <version> sm_100a" */
+const char* ddb200_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tensor-product table (one per TensorProductConvLayer; immutable after creation, shareable between streams).
+ * Blob layout (produced by diffdock_b200/tp_table.py; int32 words):
+ *   hdr[32] : 0 magic 'DB20' | 1 n_paths | 2 n_tiles | 3 n_chunks | 4 n_mentries | 5 n_terms | 6 D_in | 7 D_sh |
+ *             8 D_out | 9 sh_lmax (-1: spherical harmonics are given per edge) | 10 z_total | 11 m_total |
+ *             12 n_acc | 13 weight_numel (padded, multiple of 4) | 14 stage_floats |
+ *             15..20 word offsets of the sections below | 21 total words
+ *   paths   [n_paths][6] : in_off, mul_in, d_in, d_out, z_off, m_off
+ *   tiles   [n_tiles][8] : w_local, row_stride, n_rows, z_base, d_out, width, row_groups, acc_base
+ *   chunks  [n_chunks][4]: tile_begin, tile_end, w_offset, n_floats      (one TMA bulk copy each)
+ *   mentries[n_ment][3]  : m_index, term_begin, term_count
+ *   terms_y [n_terms]    : index into the per-edge spherical-harmonics vector
+ *   outmap  [D_out][3]   : accumulator slot, lane stride between row groups, row groups
+ * fblob: terms_val[n_terms] = path coefficient * Clebsch-Gordan entry.
+ * Replaces: the e3nn code-generated o3.FullyConnectedTensorProduct / FasterTensorProduct instances built at
+ * models/tensor_layers.py:295-299.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct ddb200_tp_table ddb200_tp_table;
+
+int  ddb200_tp_table_create(const int32_t* iblob_host, int n_ints, const float* fblob_host, int n_floats,
+                            ddb200_tp_table** out);
+void ddb200_tp_table_destroy(ddb200_tp_table* t);
+/* 0: D_in, 1: D_sh, 2: D_out, 3: weight_numel (padded), 4: sh_lmax, 5: dynamic shared memory bytes per CTA,
+ * 6: warps per CTA, 7: pipeline stages per warp */
+int  ddb200_tp_table_info(const ddb200_tp_table* t, int what);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused tensor-product convolution, accumulate phase.
+ *   for every edge e:   sum[edge_dst[e], :] += TP(x[edge_src[e], :], Y(geo[e]), w[e, :]) * edge_weight[e]
+ *                       cnt[edge_dst[e]]    += 1
+ * x        [n_src, x_stride]   gathered node irreps (x_stride >= D_in floats)
+ * edge_src [E], edge_dst [E]   int32; performance (not correctness) wants edges sorted by edge_dst (CSR order)
+ * geo      sh_lmax >= 0: edge vectors [E,3] (spherical harmonics evaluated in-kernel, component normalisation);
+ *          sh_lmax == -1: precomputed spherical harmonics [E, D_sh]
+ * edge_weight [E] or NULL
+ * w        [E, w_stride] per-edge tensor-product weights in table layout (w 16-byte aligned, w_stride % 4 == 0)
+ * sum      [n_dst, D_out] fp32 accumulator, cnt [n_dst] fp32 (may be NULL); caller zero-initialises both
+ * Replaces: models/tensor_layers.py:139-144 and :204-221 (gather, tensor product, scatter-sum, bincount), plus the
+ * o3.spherical_harmonics calls at models/cg_model.py:494,511,556-557,622,636.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_tpconv_accumulate(const ddb200_tp_table* t, const float* x, int64_t x_stride, const int32_t* edge_src,
+                             const int32_t* edge_dst, const float* geo, const float* edge_weight, const float* w,
+                             int64_t w_stride, int64_t n_edges, float* sum, float* cnt, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Convolution epilogue:  out[n, c] = (sum[n, c] / max(cnt[n], eps) if mean else sum[n, c]) * bn_scale[c] + bn_shift[c]
+ *                                    + (c < res_dim ? residual[n, c] : 0)
+ * bn_scale / bn_shift: eval-mode e3nn BatchNorm folded per column (NULL = identity); residual may be NULL.
+ * Replaces: models/tensor_layers.py:227-229 (mean), :327-328 (BatchNorm), :330-332 (zero-padded residual).
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_tpconv_finalize(const float* sum, const float* cnt, int64_t n_rows, int d_out, int mean,
+                           const float* bn_scale, const float* bn_shift, const float* residual,
+                           int64_t res_stride, int res_dim, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFDOCK_B200_H */

@@ -1,0 +1,76 @@
+"""Oracle restatement of models/layers.py and of the time embeddings in utils/diffusion_utils.py.
+TEST INFRASTRUCTURE (see oracle/__init__.py)."""
+import math
+
+import torch
+from torch import nn
+
+
+def fc_block(in_dim, hidden_dim, out_dim, layers, dropout=0.0, activation='relu'):
+    """models/layers.py:10-17 (FCBlock): Linear-act-Dropout [x(layers-2)] ... Linear.  Index layout of the
+    nn.Sequential (.0, .3, .6 ...) is kept so state_dicts are interchangeable."""
+    act = {'relu': nn.ReLU, 'silu': nn.SiLU}[activation]
+    assert layers >= 2
+    seq = [nn.Linear(in_dim, hidden_dim), act(), nn.Dropout(dropout)]
+    for _ in range(layers - 2):
+        seq += [nn.Linear(hidden_dim, hidden_dim), act(), nn.Dropout(dropout)]
+    seq += [nn.Linear(hidden_dim, out_dim)]
+    return nn.Sequential(*seq)
+
+
+class GaussianSmearing(nn.Module):
+    """models/layers.py:20-30.  coeff is a Python float taken from the fp32 linspace (hazard C.10)."""
+
+    def __init__(self, start=0.0, stop=5.0, num_gaussians=50):
+        super().__init__()
+        offset = torch.linspace(start, stop, num_gaussians)
+        self.coeff = -0.5 / (offset[1] - offset[0]).item() ** 2
+        self.register_buffer('offset', offset)
+
+    def forward(self, dist):
+        d = dist.reshape(-1, 1) - self.offset.reshape(1, -1)
+        return torch.exp(self.coeff * d * d)
+
+
+class AtomEncoder(nn.Module):
+    """models/layers.py:33-67: sum of categorical embeddings, then Linear on [emb | scalar/LM/sigma feats]."""
+
+    def __init__(self, emb_dim, feature_dims, sigma_embed_dim, lm_embedding_dim=0):
+        super().__init__()
+        self.atom_embedding_list = nn.ModuleList()
+        self.num_categorical_features = len(feature_dims[0])
+        self.additional_features_dim = feature_dims[1] + sigma_embed_dim + lm_embedding_dim
+        for dim in feature_dims[0]:
+            emb = nn.Embedding(dim, emb_dim)
+            nn.init.xavier_uniform_(emb.weight.data)
+            self.atom_embedding_list.append(emb)
+        if self.additional_features_dim > 0:
+            self.additional_features_embedder = nn.Linear(self.additional_features_dim + emb_dim, emb_dim)
+
+    def forward(self, x):
+        assert x.shape[1] == self.num_categorical_features + self.additional_features_dim
+        e = 0
+        for i in range(self.num_categorical_features):
+            e = e + self.atom_embedding_list[i](x[:, i].long())
+        if self.additional_features_dim > 0:
+            e = self.additional_features_embedder(torch.cat([e, x[:, self.num_categorical_features:].to(e.dtype)], 1))
+        return e
+
+
+def sinusoidal_embedding(timesteps, embedding_dim, max_positions=10000):
+    """utils/diffusion_utils.py:99-110."""
+    assert timesteps.dim() == 1
+    half = embedding_dim // 2
+    k = math.log(max_positions) / (half - 1)
+    freq = torch.exp(torch.arange(half, dtype=torch.float32, device=timesteps.device) * -k)
+    emb = timesteps.float()[:, None] * freq[None, :]
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], 1)
+    if embedding_dim % 2 == 1:
+        emb = torch.nn.functional.pad(emb, (0, 1))
+    return emb
+
+
+def get_timestep_embedding(embedding_type, embedding_dim, embedding_scale=10000):
+    """utils/diffusion_utils.py:128-135 ('sinusoidal' only; 'fourier' carries a random parameter W)."""
+    assert embedding_type == 'sinusoidal'
+    return lambda x: sinusoidal_embedding(embedding_scale * x, embedding_dim)

@@ -1,0 +1,40 @@
+"""GPU parity: fused tensor-product convolution (csrc/tpconv.cu through the C ABI) vs the CPU oracle layer.
+Tolerance: fp32 arithmetic with a different summation order -> 2e-5 relative to the output's max magnitude
+(north_star asks 1e-4 on scores)."""
+import pytest
+import torch
+
+from tests.parity_helpers import layer_parity_case
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2, 3])
+@pytest.mark.parametrize("lmax,faster", [(2, False), (1, True), (1, False)])
+def test_layer_matches_oracle(built_lib, stage, lmax, faster):
+    assert layer_parity_case(seed=stage, stage=stage, lmax=lmax, faster=faster) < TOL
+
+
+def test_given_sh_mode(built_lib):
+    assert layer_parity_case(seed=11, use_vec=False) < TOL
+
+
+def test_multigroup_and_edge_weights(built_lib):
+    assert layer_parity_case(seed=5, groups=4, edge_weight_tensor=True, n_edges=1500) < TOL
+
+
+def test_sum_reduce_and_out_nodes(built_lib):
+    assert layer_parity_case(seed=6, reduce='sum', out_nodes=7, n_edges=900) < TOL
+
+
+def test_skewed_degrees_and_empty_rows(built_lib):
+    # few targets receive everything; most rows stay empty -> mean of empty segment = 0 then BatchNorm shift + residual
+    assert layer_parity_case(seed=7, n_nodes=300, out_nodes=None, n_edges=5000) < TOL
+    assert layer_parity_case(seed=8, n_nodes=40, n_edges=33) < TOL
+    assert layer_parity_case(seed=9, n_nodes=40, n_edges=1) < TOL
+
+
+def test_small_config(built_lib):
+    assert layer_parity_case(seed=3, ns=16, nv=4, stage=3) < TOL
+    assert layer_parity_case(seed=4, ns=24, nv=6, stage=2, lmax=1, faster=True) < TOL
