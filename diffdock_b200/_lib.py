@@ -20,6 +20,8 @@ SIGNATURES = {
     'ddb200_tp_table_info': (_int, [_vp, _int]),
     'ddb200_tpconv_accumulate': (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'ddb200_tpconv_finalize': (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    'ddb200_radius_count': (_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _int, _int, _vp, _vp]),
+    'ddb200_radius_fill': (_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _int, _int, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -1,0 +1,363 @@
+"""Drop-in for the reference's coarse-grained score model ``models/cg_model.py:CGModel`` (score mode).
+
+Same constructor keywords, ``forward(data) -> (tr_pred, rot_pred, tor_pred, sidechain_pred)`` contract, ``state_dict``
+keys and side effects on ``data``; ``utils/sampling.py:116`` can call it unchanged.  What runs
+underneath is B200-native: neighbour search and the tensor-product convolutions (SH + Clebsch-Gordan contraction +
+segmented reduction + BatchNorm/residual epilogue) are hand-written sm_100a kernels behind the C ABI
+(include/diffdock_b200.h); every edge list is produced already CSR-sorted by its convolution target; the score-norm
+tables are device buffers (no host round trips for so3/torus look-ups).
+
+CUDA only, inference only.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .irreps import irreps_str, sh_irreps
+from .layers import AtomEncoder, GaussianSmearing
+from .synthetic import LIG_FEATURE_DIMS as lig_feature_dims, REC_RESIDUE_FEATURE_DIMS as rec_residue_feature_dims
+from .tensor_layers import TensorProductConvLayer, get_irrep_seq
+from .tp_table import full_tensor_product
+
+_TABLES = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tables', 'score_norm_tables.npz')
+# utils/so3.py:6 and utils/torus.py:25-26
+SO3_MIN_EPS, SO3_MAX_EPS, SO3_N_EPS = 0.0005, 4, 2000
+TORUS_SIGMA_MIN, TORUS_SIGMA_MAX, TORUS_SIGMA_N = 3e-3, 2, 5000
+
+
+def _mlp(n_in, n_hidden, n_out, dropout):
+    return nn.Sequential(nn.Linear(n_in, n_hidden), nn.ReLU(), nn.Dropout(dropout), nn.Linear(n_hidden, n_out))
+
+
+def _sh_l2(vec):
+    """Component-normalised l=2 real spherical harmonics of the normalised vectors (o3.spherical_harmonics("2e", ...),
+    models/cg_model.py:411)."""
+    v = torch.nn.functional.normalize(vec, dim=-1)
+    x, y, z = v[:, 0], v[:, 1], v[:, 2]
+    s5, s15 = math.sqrt(5.0), math.sqrt(15.0)
+    return torch.stack([s15 * x * z, s15 * x * y, s5 * (y * y - 0.5 * (x * x + z * z)), s15 * y * z,
+                        0.5 * s15 * (z * z - x * x)], dim=-1)
+
+
+def _sh_full(vec, lmax):
+    v = torch.nn.functional.normalize(vec, dim=-1)
+    cols = [torch.ones_like(v[:, :1])]
+    if lmax >= 1:
+        cols.append(math.sqrt(3.0) * v)
+    if lmax >= 2:
+        cols.append(_sh_l2(vec))
+    return torch.cat(cols, dim=-1)
+
+
+class CGModel(nn.Module):
+    def __init__(self, t_to_sigma, device, timestep_emb_func, in_lig_edge_features=4, sigma_embed_dim=32, sh_lmax=2,
+                 ns=16, nv=4, num_conv_layers=2, lig_max_radius=5, rec_max_radius=30, cross_max_distance=250,
+                 center_max_distance=30, distance_embed_dim=32, cross_distance_embed_dim=32, no_torsion=False,
+                 scale_by_sigma=True, norm_by_sigma=True, use_second_order_repr=False, batch_norm=True,
+                 dynamic_max_cross=False, dropout=0.0, smooth_edges=False, odd_parity=False,
+                 separate_noise_schedule=False, lm_embedding_type=None, confidence_mode=False,
+                 confidence_dropout=0, confidence_no_batchnorm=False,
+                 asyncronous_noise_schedule=False, affinity_prediction=False, parallel=1,
+                 parallel_aggregators="mean max min std", num_confidence_outputs=1, atom_num_confidence_outputs=1,
+                 fixed_center_conv=False, no_aminoacid_identities=False, include_miscellaneous_atoms=False,
+                 differentiate_convolutions=True, tp_weights_layers=2, num_prot_emb_layers=0, reduce_pseudoscalars=False,
+                 embed_also_ligand=False, atom_confidence=False, sidechain_pred=False, depthwise_convolution=False):
+        super().__init__()
+        assert parallel == 1, "not implemented"
+        unsupported = dict(confidence_mode=confidence_mode, separate_noise_schedule=separate_noise_schedule,
+                           asyncronous_noise_schedule=asyncronous_noise_schedule,
+                           include_miscellaneous_atoms=include_miscellaneous_atoms, sidechain_pred=sidechain_pred,
+                           depthwise_convolution=depthwise_convolution, atom_confidence=atom_confidence)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f"{bad}: outside the score-model hot path built so far (SURVEY.md section 8)")
+        if lm_embedding_type not in (None, 'precomputed'):
+            raise NotImplementedError("on-the-fly ESM embeddings are preprocessing (out of scope); use 'precomputed'")
+        self.t_to_sigma, self.device, self.timestep_emb_func = t_to_sigma, device, timestep_emb_func
+        self.in_lig_edge_features, self.sigma_embed_dim = in_lig_edge_features, sigma_embed_dim
+        self.lig_max_radius, self.rec_max_radius = lig_max_radius, rec_max_radius
+        self.cross_max_distance, self.dynamic_max_cross = cross_max_distance, dynamic_max_cross
+        self.center_max_distance = center_max_distance
+        self.distance_embed_dim, self.cross_distance_embed_dim = distance_embed_dim, cross_distance_embed_dim
+        self.sh_lmax = sh_lmax
+        self.sh_irreps = irreps_str(sh_irreps(sh_lmax))
+        self.ns, self.nv = ns, nv
+        self.scale_by_sigma, self.norm_by_sigma = scale_by_sigma, norm_by_sigma
+        self.no_torsion, self.smooth_edges, self.odd_parity = no_torsion, smooth_edges, odd_parity
+        self.confidence_mode = False
+        self.num_conv_layers, self.num_prot_emb_layers = num_conv_layers, num_prot_emb_layers
+        self.fixed_center_conv, self.no_aminoacid_identities = fixed_center_conv, no_aminoacid_identities
+        self.differentiate_convolutions, self.reduce_pseudoscalars = differentiate_convolutions, reduce_pseudoscalars
+        self.embed_also_ligand = embed_also_ligand
+        self.lm_embedding_type = lm_embedding_type
+        lm_dim = 1280 if lm_embedding_type == 'precomputed' else 0
+        S, D, Dx = sigma_embed_dim, distance_embed_dim, cross_distance_embed_dim
+
+        self.lig_node_embedding = AtomEncoder(emb_dim=ns, feature_dims=lig_feature_dims, sigma_embed_dim=S)
+        self.lig_edge_embedding = _mlp(in_lig_edge_features + S + D, ns, ns, dropout)
+        self.rec_node_embedding = AtomEncoder(emb_dim=ns, feature_dims=rec_residue_feature_dims, sigma_embed_dim=0,
+                                              lm_embedding_dim=lm_dim)
+        self.rec_edge_embedding = _mlp(D, ns, ns, dropout)
+        self.rec_sigma_embedding = _mlp(S, ns, ns, dropout)
+        self.cross_edge_embedding = _mlp(S + Dx, ns, ns, dropout)
+        self.lig_distance_expansion = GaussianSmearing(0.0, lig_max_radius, D)
+        self.rec_distance_expansion = GaussianSmearing(0.0, rec_max_radius, D)
+        self.cross_distance_expansion = GaussianSmearing(0.0, cross_max_distance, Dx)
+
+        seq = get_irrep_seq(ns, nv, use_second_order_repr, reduce_pseudoscalars)
+        faster = sh_lmax == 1 and not use_second_order_repr
+
+        def conv(i, groups):
+            return TensorProductConvLayer(in_irreps=seq[min(i, len(seq) - 1)], sh_irreps=self.sh_irreps,
+                                          out_irreps=seq[min(i + 1, len(seq) - 1)], n_edge_features=3 * ns,
+                                          hidden_features=3 * ns, residual=True, batch_norm=batch_norm, dropout=dropout,
+                                          faster=faster, tp_weights_layers=tp_weights_layers, edge_groups=groups)
+
+        self.rec_emb_layers = nn.ModuleList([conv(i, 1) for i in range(num_prot_emb_layers)])
+        if embed_also_ligand:
+            self.lig_emb_layers = nn.ModuleList([conv(i, 1) for i in range(num_prot_emb_layers)])
+        last = num_prot_emb_layers + num_conv_layers - 1
+        self.conv_layers = nn.ModuleList([
+            conv(i, 1 if not differentiate_convolutions else (2 if i == last else 4))
+            for i in range(num_prot_emb_layers, num_prot_emb_layers + num_conv_layers)])
+
+        # translation / rotation head
+        self.center_distance_expansion = GaussianSmearing(0.0, center_max_distance, D)
+        self.center_edge_embedding = _mlp(D + S, ns, ns, dropout)
+        self.final_conv = TensorProductConvLayer(in_irreps=self.conv_layers[-1].out_irreps, sh_irreps=self.sh_irreps,
+                                                 out_irreps='2x1o + 2x1e' if not odd_parity else '1x1o + 1x1e',
+                                                 n_edge_features=2 * ns, residual=False, dropout=dropout,
+                                                 batch_norm=batch_norm)
+        self.tr_final_layer = nn.Sequential(nn.Linear(1 + S, ns), nn.Dropout(dropout), nn.ReLU(), nn.Linear(ns, 1))
+        self.rot_final_layer = nn.Sequential(nn.Linear(1 + S, ns), nn.Dropout(dropout), nn.ReLU(), nn.Linear(ns, 1))
+        if not no_torsion:
+            self.final_edge_embedding = _mlp(D, ns, ns, dropout)
+            T, tor_sh = full_tensor_product(self.sh_irreps, '1x2e')       # o3.FullTensorProduct(sh, "2e"), :240
+            self.register_buffer('_tor_tp', torch.from_numpy(T).float(), persistent=False)
+            self.tor_bond_conv = TensorProductConvLayer(in_irreps=self.conv_layers[-1].out_irreps,
+                                                        sh_irreps=irreps_str(tor_sh),
+                                                        out_irreps=f'{ns}x0o + {ns}x0e' if not odd_parity else f'{ns}x0o',
+                                                        n_edge_features=3 * ns, residual=False, dropout=dropout,
+                                                        batch_norm=batch_norm)
+            self.tor_final_layer = nn.Sequential(nn.Linear(2 * ns if not odd_parity else ns, ns, bias=False), nn.Tanh(),
+                                                 nn.Dropout(dropout), nn.Linear(ns, 1, bias=False))
+        # score-norm tables (utils/so3.py:59, utils/torus.py:72-76) as device buffers; not part of the state_dict
+        z = np.load(_TABLES)
+        self.register_buffer('_so3_table', torch.from_numpy(z['so3_exp_score_norms']).float(), persistent=False)
+        self.register_buffer('_torus_table', torch.from_numpy(z['torus_score_norm']).float(), persistent=False)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts reference checkpoints: e3nn's TensorProduct modules register buffers (``*.tp.weight``,
+        ``*.tp.output_mask``, ``final_tp_tor.*``, compiled ``_w3j_*`` constants) that have no counterpart here."""
+        drop = [k for k in state_dict if '.tp.' in k or k.startswith('final_tp_tor.') or '_w3j' in k]
+        if drop:
+            state_dict = {k: v for k, v in state_dict.items() if k not in drop}
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def set_score_norm_tables(self, so3_exp_score_norms, torus_score_norm):
+        """Install the tables of the caller's reference installation (torus.score_norm_ is a Monte-Carlo estimate that
+        differs per machine)."""
+        self._so3_table.copy_(torch.as_tensor(so3_exp_score_norms, dtype=torch.float32))
+        self._torus_table.copy_(torch.as_tensor(torus_score_norm, dtype=torch.float32))
+
+    # ---------------------------------------------------------------------------------------------------------
+    def get_edge_weight(self, edge_vec, max_norm):
+        if self.smooth_edges:
+            nrm = torch.clip(edge_vec.norm(dim=-1) * np.pi / max_norm, max=np.pi)
+            return 0.5 * (torch.cos(nrm) + 1.0).unsqueeze(-1)
+        return 1.0
+
+    def _so3_score_norm(self, eps):
+        """utils/so3.py:89-93 evaluated on the device (fp32 index arithmetic, round-half-even like np.around)."""
+        lo, hi = math.log10(SO3_MIN_EPS), math.log10(SO3_MAX_EPS)
+        idx = (torch.log10(eps.float()) - np.float32(lo)) / np.float32(hi - lo) * SO3_N_EPS
+        idx = torch.round(idx).clamp(0, SO3_N_EPS - 1).long()
+        return self._so3_table[idx]
+
+    def _torus_score_norm(self, sigma):
+        """utils/torus.py:79-83 on the device."""
+        lo, hi = math.log(TORUS_SIGMA_MIN), math.log(TORUS_SIGMA_MAX)
+        s = torch.log(sigma.float() / np.float32(np.pi))
+        s = (s - np.float32(lo)) / np.float32(hi - lo) * TORUS_SIGMA_N
+        s = torch.round(s.clamp(0, TORUS_SIGMA_N)).long()
+        return self._torus_table[s]
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _static(self, data):
+        """Pose-independent quantities, cached on ``data`` like the reference does (models/cg_model.py:273,292-295)."""
+        rec, rr, lig, ll = data['receptor'], data['receptor', 'receptor'], data['ligand'], data['ligand', 'ligand']
+        if hasattr(rec, 'rec_node_attr') and hasattr(rr, '_b200'):
+            return rr._b200
+        B = data.num_graphs
+        c = {}
+        ei = rr.edge_index.long()
+        vec = (rec.pos[ei[1]] - rec.pos[ei[0]]).float()
+        rec_edge_attr = self.rec_edge_embedding(self.rec_distance_expansion(vec.norm(dim=-1)))
+        rec_node_attr = self.rec_node_embedding(rec.x)
+        ew = self.get_edge_weight(vec, self.rec_max_radius)
+        for layer in self.rec_emb_layers:
+            ea_ = torch.cat([rec_edge_attr, rec_node_attr[ei[0], :self.ns], rec_node_attr[ei[1], :self.ns]], -1)
+            rec_node_attr = layer(rec_node_attr, ei, ea_, None, edge_weight=ew, edge_vec=vec)
+        rec.rec_node_attr, rr.rec_edge_attr, rr.edge_weight = rec_node_attr, rec_edge_attr, ew
+        rr.edge_sh = None   # evaluated inside the convolution kernel from the edge vectors; kept for attribute parity
+        # CSR order of the static receptor graph (target = edge_index[0])
+        tgt, order = torch.sort(ei[0], stable=True)
+        c['rr_tgt'], c['rr_src'] = tgt, ei[1][order]
+        c['rr_vec'] = vec[order].contiguous()
+        c['rr_ea'] = rec_edge_attr[order].contiguous()
+        c['rr_ew'] = ew[order].contiguous() if torch.is_tensor(ew) else None
+        c['rr_tgt_batch'] = rec.batch[tgt]
+        c['rec_ptr'] = ops.segment_ptr(rec.batch, B)
+        c['lig_ptr'] = ops.segment_ptr(lig.batch, B)
+        # rotatable bonds are static too
+        mask = lig.edge_mask
+        bonds = ll.edge_index[:, mask].long()
+        c['bonds'], c['n_bonds'] = bonds, int(bonds.shape[1])
+        c['bond_batch'] = lig.batch[bonds[0]] if bonds.shape[1] else None
+        rr._b200 = c
+        return c
+
+    def _ligand_graph(self, data, c):
+        """Bond edges + radius graph, sorted by convolution target (models/cg_model.py:467-497)."""
+        lig, ll = data['ligand'], data['ligand', 'ligand']
+        lig.node_sigma_emb = self.timestep_emb_func(lig.node_t['tr'])
+        pos = lig.pos.float()
+        centre, nbr, _ = ops.radius(pos, pos, c['lig_ptr'], lig.batch, r=self.lig_max_radius,
+                                    max_num_neighbors=33, exclude_self=True)      # radius_graph: cap 32 (+ self)
+        n_rad = nbr.shape[0]
+        row0 = torch.cat([ll.edge_index[0].long(), nbr.long()])      # target of the convolution
+        row1 = torch.cat([ll.edge_index[1].long(), centre.long()])   # gathered node
+        bond_attr = torch.cat([ll.edge_attr.float(),
+                               torch.zeros(n_rad, self.in_lig_edge_features, device=pos.device)], 0)
+        tgt, order = torch.sort(row0, stable=True)
+        src = row1[order]
+        vec = pos[src] - pos[tgt]
+        edge_attr = torch.cat([bond_attr[order], lig.node_sigma_emb[tgt], self.lig_distance_expansion(vec.norm(dim=-1))], 1)
+        node_attr = torch.cat([lig.x.float(), lig.node_sigma_emb], 1)
+        return node_attr, tgt, src, edge_attr, vec, self.get_edge_weight(vec, self.lig_max_radius)
+
+    def _cross_graph(self, data, c, cutoff):
+        """Ligand-receptor edges within the (per-complex) cutoff, sorted by ligand atom (models/cg_model.py:539-562)."""
+        lig, rec = data['ligand'], data['receptor']
+        lp, rp = lig.pos.float(), rec.pos.float()
+        if torch.is_tensor(cutoff):
+            li, ri, _ = ops.radius(rp, lp, c['rec_ptr'], lig.batch, r=1.0, r_per_graph=cutoff.reshape(-1),
+                                   max_num_neighbors=10000)
+        else:
+            li, ri, _ = ops.radius(rp, lp, c['rec_ptr'], lig.batch, r=float(cutoff), max_num_neighbors=10000)
+        li, ri = li.long(), ri.long()
+        vec = rp[ri] - lp[li]
+        edge_attr = torch.cat([lig.node_sigma_emb[li], self.cross_distance_expansion(vec.norm(dim=-1))], 1)
+        cutoff_d = cutoff.reshape(-1)[lig.batch[li]] if torch.is_tensor(cutoff) else cutoff
+        return li, ri, edge_attr, vec, self.get_edge_weight(vec, cutoff_d)
+
+    # ---------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, data):
+        if self.training:
+            raise RuntimeError("diffdock_b200.CGModel is inference-only: call .eval()")
+        lig, rec = data['ligand'], data['receptor']
+        if not lig.pos.is_cuda:
+            raise RuntimeError("diffdock_b200.CGModel runs on CUDA tensors only (no CPU fallback): data.to('cuda')")
+        if self.no_aminoacid_identities:
+            rec.x = rec.x * 0
+        ns, B = self.ns, data.num_graphs
+        tr_sigma, rot_sigma, tor_sigma = self.t_to_sigma(*[data.complex_t[k] for k in ('tr', 'rot', 'tor')])
+        c = self._static(data)
+
+        # -- embeddings (models/cg_model.py:272-306) --------------------------------------------------------------
+        sig = self.rec_sigma_embedding(self.timestep_emb_func(data.complex_t['tr']))
+        rec_node = rec.rec_node_attr.clone()
+        rec_node[:, :ns] += sig[rec.batch]
+        rr_ea = c['rr_ea'] + sig[c['rr_tgt_batch']]
+        lig_x, ll_tgt, ll_src, ll_ea, ll_vec, ll_ew = self._ligand_graph(data, c)
+        lig_node = self.lig_node_embedding(lig_x)
+        ll_ea = self.lig_edge_embedding(ll_ea)
+        assert self.embed_also_ligand, "otherwise reimplement padding"
+        ll_ei = torch.stack([ll_tgt, ll_src])
+        for layer in self.lig_emb_layers:
+            ea_ = torch.cat([ll_ea, lig_node[ll_tgt, :ns], lig_node[ll_src, :ns]], -1)
+            lig_node = layer(lig_node, ll_ei, ea_, None, edge_weight=ll_ew, edge_vec=ll_vec, assume_sorted=True)
+
+        # -- cross graph (:321-327) ---------------------------------------------------------------------------------
+        cutoff = (tr_sigma * 3 + 20).unsqueeze(1) if self.dynamic_max_cross else self.cross_max_distance
+        li, ri, lr_ea, lr_vec, lr_ew = self._cross_graph(data, c, cutoff)
+        lr_ea = self.cross_edge_embedding(lr_ea)
+
+        # -- joint graph: four edge groups, each CSR-sorted by target (:329-338) ------------------------------------
+        n_lig = lig_node.shape[0]
+        node = torch.cat([lig_node, rec_node], 0)
+        rl_tgt, rev = torch.sort(ri, stable=True)            # receptor <- ligand direction: same pairs, sorted by residue
+        groups = [
+            (ll_tgt, ll_src, ll_ea, ll_vec, ll_ew),                                             # lig <- lig
+            (li, ri + n_lig, lr_ea, lr_vec, lr_ew),                                             # lig <- rec
+            (c['rr_tgt'] + n_lig, c['rr_src'] + n_lig, rr_ea, c['rr_vec'], c['rr_ew']),         # rec <- rec
+            (rl_tgt + n_lig, li[rev], lr_ea[rev], -lr_vec[rev],
+             lr_ew[rev] if torch.is_tensor(lr_ew) else lr_ew),                                  # rec <- lig, SH(-v)
+        ]
+        smooth = self.smooth_edges
+        L = len(self.conv_layers)
+        for l, layer in enumerate(self.conv_layers):
+            use = groups if l < L - 1 else groups[:2]       # last layer: only edges that end on ligand atoms (:347-349)
+            tgt = torch.cat([g[0] for g in use])
+            src = torch.cat([g[1] for g in use])
+            vec = torch.cat([g[3] for g in use])
+            ew = torch.cat([g[4] if torch.is_tensor(g[4]) else torch.ones((g[0].shape[0], 1), device=node.device)
+                            for g in use]) if smooth else 1.0
+            ea = [torch.cat([g[2], node[g[0], :ns], node[g[1], :ns]], -1) for g in use]
+            if not self.differentiate_convolutions:
+                ea = torch.cat(ea, 0)
+            node = layer(node, torch.stack([tgt, src]), ea, None, edge_weight=ew, edge_vec=vec, assume_sorted=True)
+        lig_node = node[:n_lig]
+
+        # -- translation / rotation head (:368-395) -----------------------------------------------------------------
+        pos = lig.pos.float()
+        arange = torch.arange(n_lig, device=pos.device)
+        center = torch.zeros((B, 3), device=pos.device).index_add_(0, lig.batch, pos)
+        center = center / torch.bincount(lig.batch, minlength=B).unsqueeze(1)
+        c_vec = pos - center[lig.batch]
+        c_ea = torch.cat([self.center_distance_expansion(c_vec.norm(dim=-1)), lig.node_sigma_emb], 1)
+        c_ea = self.center_edge_embedding(c_ea)
+        idx = arange if self.fixed_center_conv else lig.batch            # hazard C.6: graph id indexes lig_node
+        c_ea = torch.cat([c_ea, lig_node[idx, :ns]], -1)
+        glob = self.final_conv(lig_node, torch.stack([lig.batch, arange]), c_ea, None, out_nodes=B, edge_vec=c_vec,
+                               assume_sorted=True)
+        tr_pred = glob[:, :3] + (glob[:, 6:9] if not self.odd_parity else 0)
+        rot_pred = glob[:, 3:6] + (glob[:, 9:] if not self.odd_parity else 0)
+        data.graph_sigma_emb = self.timestep_emb_func(data.complex_t['tr'])
+        tr_norm = torch.linalg.vector_norm(tr_pred, dim=1).unsqueeze(1)
+        tr_pred = tr_pred / tr_norm * self.tr_final_layer(torch.cat([tr_norm, data.graph_sigma_emb], dim=1))
+        rot_norm = torch.linalg.vector_norm(rot_pred, dim=1).unsqueeze(1)
+        rot_pred = rot_pred / rot_norm * self.rot_final_layer(torch.cat([rot_norm, data.graph_sigma_emb], dim=1))
+        if self.scale_by_sigma:
+            tr_pred = tr_pred / tr_sigma.unsqueeze(1)
+            rot_pred = rot_pred * self._so3_score_norm(rot_sigma).unsqueeze(1)
+
+        if self.no_torsion or c['n_bonds'] == 0:
+            return tr_pred, rot_pred, torch.empty(0, device=self.device), None
+
+        # -- torsion head (:406-423) --------------------------------------------------------------------------------
+        bonds = c['bonds']
+        bond_pos = (pos[bonds[0]] + pos[bonds[1]]) / 2
+        bi, ai, _ = ops.radius(pos, bond_pos, c['lig_ptr'], c['bond_batch'], r=self.lig_max_radius, max_num_neighbors=32)
+        bi, ai = bi.long(), ai.long()
+        t_vec = pos[ai] - bond_pos[bi]
+        t_ea = self.final_edge_embedding(self.lig_distance_expansion(t_vec.norm(dim=-1)))
+        bond_vec = pos[bonds[1]] - pos[bonds[0]]
+        bond_attr = lig_node[bonds[0]] + lig_node[bonds[1]]
+        t_sh = torch.einsum('ea,eb,abc->ec', _sh_full(t_vec, self.sh_lmax), _sh_l2(bond_vec)[bi], self._tor_tp)
+        t_ea = torch.cat([t_ea, lig_node[ai, :ns], bond_attr[bi, :ns]], -1)
+        tor_pred = self.tor_bond_conv(lig_node, torch.stack([bi, ai]), t_ea, t_sh, out_nodes=c['n_bonds'], reduce='mean',
+                                      edge_weight=self.get_edge_weight(t_vec, self.lig_max_radius), assume_sorted=True)
+        tor_pred = self.tor_final_layer(tor_pred).squeeze(1)
+        edge_sigma = tor_sigma[lig.batch][data['ligand', 'ligand'].edge_index[0]][lig.edge_mask]
+        if self.scale_by_sigma:
+            tor_pred = tor_pred * torch.sqrt(self._torus_score_norm(edge_sigma))
+        return tr_pred, rot_pred, tor_pred, None

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams
   float* racc = zs + ((z_total + 3) & ~3);                     // n_acc * 32
   uint64_t* mybar = bars + warp * p.stages;
   for (int i = lane; i < n_acc * WARP; i += WARP) racc[i] = 0.f;
+  for (int i = lane; i < m_total; i += WARP) ms[i] = 0.f;   // structurally-zero CG entries are never rewritten
+  __syncwarp();
 
   const long long E = p.n_edges;
   const long long n_units = (E + ERUN - 1) / ERUN;

@@ -168,3 +168,20 @@ def collate(data_list: List[HeteroGraph]) -> HeteroGraph:
             out._globals[k] = vals
     out._globals['num_graphs'] = B
     return out
+
+
+def graph_to_dict(g: HeteroGraph) -> dict:
+    """Plain nested dict (tensors / numpy / str) for fixtures."""
+    return {'nodes': {k: dict(s.__dict__) for k, s in g._nodes.items()},
+            'edges': {k: dict(s.__dict__) for k, s in g._edges.items()},
+            'globals': dict(g._globals)}
+
+
+def graph_from_dict(d: dict) -> HeteroGraph:
+    g = HeteroGraph()
+    for k, s in d['nodes'].items():
+        g._nodes[k] = Store(**s)
+    for k, s in d['edges'].items():
+        g._edges[tuple(k)] = Store(**s)
+    g._globals.update(d['globals'])
+    return g

@@ -1,0 +1,49 @@
+"""Embedding layers with the reference's parameter names (models/layers.py) - plain PyTorch modules on the device
+(small dense ops; the hot convolution lives in csrc/)."""
+import torch
+from torch import nn
+
+from .tensor_layers import FCBlock  # noqa: F401  (re-export: the reference keeps FCBlock in models/layers.py)
+
+
+class GaussianSmearing(nn.Module):
+    """Radial basis expansion exp(coeff * (d - mu_k)^2), mu = linspace(start, stop, K)  (models/layers.py:20-30)."""
+
+    def __init__(self, start=0.0, stop=5.0, num_gaussians=50):
+        super().__init__()
+        mu = torch.linspace(start, stop, num_gaussians)
+        self.coeff = -0.5 / (mu[1] - mu[0]).item() ** 2
+        self.register_buffer('offset', mu)
+
+    def forward(self, dist):
+        diff = dist.reshape(-1, 1) - self.offset.reshape(1, -1)
+        return torch.exp(self.coeff * diff * diff)
+
+
+class AtomEncoder(nn.Module):
+    """Sum of one embedding table per categorical column, then a Linear over [embedding | remaining float columns]
+    (models/layers.py:33-67)."""
+
+    def __init__(self, emb_dim, feature_dims, sigma_embed_dim, lm_embedding_dim=0):
+        super().__init__()
+        cat_dims, n_scalar = feature_dims
+        self.num_categorical_features = len(cat_dims)
+        self.additional_features_dim = n_scalar + sigma_embed_dim + lm_embedding_dim
+        self.atom_embedding_list = nn.ModuleList()
+        for d in cat_dims:
+            table = nn.Embedding(d, emb_dim)
+            nn.init.xavier_uniform_(table.weight.data)
+            self.atom_embedding_list.append(table)
+        if self.additional_features_dim > 0:
+            self.additional_features_embedder = nn.Linear(self.additional_features_dim + emb_dim, emb_dim)
+
+    def forward(self, x):
+        nc = self.num_categorical_features
+        assert x.shape[1] == nc + self.additional_features_dim
+        idx = x[:, :nc].long()
+        h = self.atom_embedding_list[0](idx[:, 0])
+        for i in range(1, nc):
+            h = h + self.atom_embedding_list[i](idx[:, i])
+        if self.additional_features_dim > 0:
+            h = self.additional_features_embedder(torch.cat([h, x[:, nc:].to(h.dtype)], dim=1))
+        return h

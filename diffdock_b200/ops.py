@@ -88,3 +88,38 @@ def tpconv_finalize(sum_buf, cnt_buf, mean, bn_scale=None, bn_shift=None, residu
                                            _ptr(bn_shift), _ptr(residual), res_stride, res_dim, _ptr(out), _stream())
     _lib.check(rc, 'ddb200_tpconv_finalize')
     return out
+
+
+def segment_ptr(batch, num_graphs):
+    """CSR offsets [B+1] (int32) of a sorted batch vector."""
+    counts = torch.bincount(batch, minlength=num_graphs)
+    ptr = torch.zeros(num_graphs + 1, dtype=torch.int32, device=batch.device)
+    ptr[1:] = torch.cumsum(counts, 0)
+    return ptr
+
+
+def radius(x, y, x_ptr, y_batch, r=1.0, r_per_graph=None, max_num_neighbors=32, exclude_self=False):
+    """Neighbour pairs (row = index into y, col = index into x), int32, sorted by (row, col).
+    Semantics of torch_cluster.radius(x, y, r, batch_x, batch_y, max_num_neighbors)."""
+    _need_cuda(x, y, x_ptr, y_batch)
+    x, y = x.float().contiguous(), y.float().contiguous()
+    yb = y_batch.to(torch.int32).contiguous()
+    n_y = y.shape[0]
+    if r_per_graph is not None:
+        r_per_graph = r_per_graph.reshape(-1).float().contiguous()
+    count = torch.empty(n_y, dtype=torch.int32, device=x.device)
+    L = _lib.lib()
+    rc = L.ddb200_radius_count(_ptr(x), _ptr(y), _ptr(x_ptr), _ptr(yb), _ptr(r_per_graph), float(r), n_y,
+                               int(max_num_neighbors), int(exclude_self), _ptr(count), _stream())
+    _lib.check(rc, 'ddb200_radius_count')
+    incl = torch.cumsum(count, 0, dtype=torch.int32)
+    row_start = (incl - count).contiguous()
+    n_edges = int(incl[-1].item()) if n_y else 0      # host sync: the edge count sizes the output buffers
+    row = torch.empty(n_edges, dtype=torch.int32, device=x.device)
+    col = torch.empty(n_edges, dtype=torch.int32, device=x.device)
+    if n_edges:
+        rc = L.ddb200_radius_fill(_ptr(x), _ptr(y), _ptr(x_ptr), _ptr(yb), _ptr(r_per_graph), float(r), n_y,
+                                  int(max_num_neighbors), int(exclude_self), _ptr(row_start), _ptr(row), _ptr(col),
+                                  _stream())
+        _lib.check(rc, 'ddb200_radius_fill')
+    return row, col, count

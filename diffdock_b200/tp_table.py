@@ -330,3 +330,32 @@ def evaluate(t: TpTable, x, sh_or_vec, w_padded, edge_weight=None):
         for o, (base, stride, R) in enumerate(outmap):
             out[e, o] = sum(racc[base + r * stride] for r in range(R))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+def full_tensor_product(irreps_1, irreps_2):
+    """Dense form of e3nn's ``o3.FullTensorProduct(irreps_1, irreps_2)`` (models/cg_model.py:240): returns
+    (T [D1, D2, D_out] float64, out_irreps) with  out[c] = sum_ab T[a,b,c] x1[a] x2[b].  One 'uvuv' instruction per
+    allowed (i1, i2, l_out) with coefficient sqrt(2 l_out + 1); output irreps sorted by (l, parity) with odd first,
+    stably, as e3nn's Irreps.sort does on (l, p) tuples."""
+    a, b = parse_irreps(irreps_1), parse_irreps(irreps_2)
+    offa, offb = irreps_offsets(a), irreps_offsets(b)
+    items = []
+    for i, (m1, l1, p1) in enumerate(a):
+        for j, (m2, l2, p2) in enumerate(b):
+            for l3 in range(abs(l1 - l2), l1 + l2 + 1):
+                items.append((i, j, m1 * m2, l3, p1 * p2))
+    order = sorted(range(len(items)), key=lambda q: (items[q][3], items[q][4], q))
+    out_irreps = [(items[q][2], items[q][3], items[q][4]) for q in order]
+    offo = irreps_offsets(out_irreps)
+    T = np.zeros((irreps_dim(a), irreps_dim(b), irreps_dim(out_irreps)))
+    for pos, q in enumerate(order):
+        i, j, mul, l3, _ = items[q]
+        (m1, l1, _), (m2, l2, _) = a[i], b[j]
+        C = real_cg(l1, l2, l3) * math.sqrt(2 * l3 + 1)
+        for u in range(m1):
+            for v in range(m2):
+                o0 = offo[pos] + (u * m2 + v) * (2 * l3 + 1)
+                T[offa[i] + u * (2 * l1 + 1):offa[i] + (u + 1) * (2 * l1 + 1),
+                  offb[j] + v * (2 * l2 + 1):offb[j] + (v + 1) * (2 * l2 + 1), o0:o0 + 2 * l3 + 1] += C
+    return T, out_irreps

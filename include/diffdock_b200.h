@@ -82,6 +82,22 @@ int ddb200_tpconv_finalize(const float* sum, const float* cnt, int64_t n_rows, i
                            const float* bn_scale, const float* bn_shift, const float* residual,
                            int64_t res_stride, int res_dim, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched fixed-radius neighbour search, two passes (count -> caller's exclusive scan -> fill).
+ * x [n_x,3] candidates, batch-sorted, x_ptr [B+1] their per-complex segment offsets; y [n_y,3] queries with
+ * y_batch [n_y] complex ids.  r_per_graph != NULL: coordinates are divided by r_per_graph[b] and compared with r
+ * (the reference's radius(x / c, y / c, 1) formulation of a per-complex cutoff); else plain radius r.
+ * Strict test d^2 < r^2; at most max_neighbors hits per query, first ones in candidate order; exclude_self drops
+ * i == j after it was counted against the cap (radius_graph semantics).  Output sorted by (query, candidate).
+ * Replaces: torch_cluster.radius / radius_graph at models/cg_model.py:477,543-548,630.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_radius_count(const float* x, const float* y, const int32_t* x_ptr, const int32_t* y_batch,
+                        const float* r_per_graph, float r, int64_t n_y, int max_neighbors, int exclude_self,
+                        int32_t* count, void* stream);
+int ddb200_radius_fill(const float* x, const float* y, const int32_t* x_ptr, const int32_t* y_batch,
+                       const float* r_per_graph, float r, int64_t n_y, int max_neighbors, int exclude_self,
+                       const int32_t* row_start, int32_t* out_row, int32_t* out_col, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

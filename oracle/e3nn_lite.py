@@ -331,10 +331,10 @@ class TensorProduct(torch.nn.Module):
                 r = torch.einsum('ijk,zuvij->zuvk', C, xx)
             else:
                 raise NotImplementedError(ins.mode)
-            r = ins.path_weight * r.reshape(Z, -1)
+            r = ins.path_weight * r.reshape(Z, mio.dim)
             out[ins.i_out] = r if out[ins.i_out] is None else out[ins.i_out] + r
         out = [o if o is not None else x1.new_zeros(Z, self.irreps_out[i].dim) for i, o in enumerate(out)]
-        return torch.cat(out, dim=-1).reshape(*lead, -1)
+        return torch.cat(out, dim=-1).reshape(*lead, self.irreps_out.dim)
 
 
 class FullyConnectedTensorProduct(TensorProduct):

@@ -43,7 +43,8 @@ def radius(x, y, r, batch_x=None, batch_y=None, max_num_neighbors=32):
     step = max(1, 2_000_000 // max(1, x.shape[0]))
     for s in range(0, y.shape[0], step):
         yy = y[s:s + step]
-        d2 = ((yy[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+        d = x[None, :, :] - yy[:, None, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]   # fixed evaluation order
         ok = (d2 < r2) & (batch_y[s:s + step, None] == batch_x[None, :])
         if max_num_neighbors < x.shape[0]:
             rank = torch.cumsum(ok.to(torch.int64), dim=1)

@@ -33,13 +33,14 @@ def rel_err(a, b):
 
 
 def layer_parity_case(seed=0, n_nodes=64, n_edges=700, ns=48, nv=10, lmax=2, stage=3, groups=1, faster=False,
-                      device='cuda:0', reduce='mean', use_vec=True, edge_weight_tensor=False, out_nodes=None):
+                      device='cuda:0', reduce='mean', use_vec=True, edge_weight_tensor=False, out_nodes=None,
+                      residual=True):
     from oracle import e3nn_lite as o3
     from oracle.tensor_layers import get_irrep_seq
     seq = get_irrep_seq(ns, nv, False, False)
     sh_irreps = str(o3.Irreps.spherical_harmonics(lmax))
     o, p = make_layer_pair(seq[min(stage, 3)], sh_irreps, seq[min(stage + 1, 3)], 3 * ns, seed=seed,
-                           hidden_features=3 * ns, edge_groups=groups, faster=faster)
+                           hidden_features=3 * ns, edge_groups=groups, faster=faster, residual=residual)
     g = torch.Generator().manual_seed(seed + 2)
     x = torch.randn(n_nodes, o3.Irreps(seq[min(stage, 3)]).dim, generator=g)
     n_tgt = out_nodes or n_nodes
@@ -63,3 +64,94 @@ def layer_parity_case(seed=0, n_nodes=64, n_edges=700, ns=48, nv=10, lmax=2, sta
             edge_vec=dev(vec) if use_vec else None)
     torch.cuda.synchronize()
     return rel_err(got, ref)
+
+
+def make_model_pair(args, seed=0, lm=True):
+    """(oracle CGModel on CPU, product CGModel) sharing one random state_dict (BatchNorm statistics randomised)."""
+    from functools import partial
+    from oracle.cg_model import CGModel as OModel
+    from oracle.layers import get_timestep_embedding as o_emb
+    from oracle.diffusion import t_to_sigma as o_t2s
+    from diffdock_b200.cg_model import CGModel as PModel
+    from diffdock_b200.diffusion_utils import get_timestep_embedding as p_emb, t_to_sigma as p_t2s
+    kw = dict(sigma_embed_dim=args.sigma_embed_dim, sh_lmax=args.sh_lmax, ns=args.ns, nv=args.nv,
+              num_conv_layers=args.num_conv_layers, lig_max_radius=args.max_radius, rec_max_radius=args.rec_max_radius,
+              cross_max_distance=args.cross_max_distance, center_max_distance=args.center_max_distance,
+              distance_embed_dim=args.distance_embed_dim, cross_distance_embed_dim=args.cross_distance_embed_dim,
+              dynamic_max_cross=args.dynamic_max_cross, lm_embedding_type='precomputed' if lm else None,
+              embed_also_ligand=True, num_prot_emb_layers=args.num_prot_emb_layers,
+              use_second_order_repr=args.use_second_order_repr, no_torsion=args.no_torsion,
+              smooth_edges=args.smooth_edges, fixed_center_conv=args.fixed_center_conv,
+              reduce_pseudoscalars=args.reduce_pseudoscalars,
+              differentiate_convolutions=args.differentiate_convolutions)
+    torch.manual_seed(seed)
+    o = OModel(partial(o_t2s, args=args), 'cpu', o_emb('sinusoidal', args.sigma_embed_dim, args.embedding_scale), **kw).eval()
+    gen = torch.Generator().manual_seed(seed + 1)
+    for m in o.modules():
+        if m.__class__.__name__ == 'BatchNorm':
+            rand_bn_(m, gen)
+    p = PModel(partial(p_t2s, args=args), torch.device('cuda:0'),
+               p_emb('sinusoidal', args.sigma_embed_dim, args.embedding_scale), **kw).eval()
+    p.load_state_dict(o.state_dict(), strict=True)     # includes e3nn-style tp.* buffers, which must be accepted
+    return o, p.to('cuda:0')
+
+
+def model_parity_case(seed=0, lmax=2, ns=16, nv=4, n_layers=3, emb=16, n_res=60, n_atoms=12, n_poses=3, t=0.5, **over):
+    from diffdock_b200.synthetic import default_model_args, make_pose_list
+    from diffdock_b200.hetero import collate
+    from oracle.diffusion import set_time
+    args = default_model_args(ns=ns, nv=nv, sh_lmax=lmax, num_conv_layers=n_layers, distance_embed_dim=emb,
+                              cross_distance_embed_dim=emb, sigma_embed_dim=emb, **over)
+    o, p = make_model_pair(args, seed)
+    poses = make_pose_list(n_poses, n_res=n_res, n_atoms=n_atoms, seed=seed + 3, tr_sigma_max=args.tr_sigma_max * t)
+    g_cpu = collate(poses)
+    g_gpu = collate(poses).to('cuda:0')
+    set_time(g_cpu, t, t, t, n_poses, 'cpu')
+    set_time(g_gpu, t, t, t, n_poses, 'cuda:0')
+    with torch.no_grad():
+        ref = o(g_cpu)
+    got = p(g_gpu)
+    torch.cuda.synchronize()
+    errs = {'tr': rel_err(got[0], ref[0]), 'rot': rel_err(got[1], ref[1]), 'tor_numel': int(ref[2].numel())}
+    assert got[2].numel() == ref[2].numel()
+    if ref[2].numel():
+        errs['tor'] = rel_err(got[2], ref[2])
+    errs = {k: v for k, v in errs.items()}
+    if errs['tor_numel'] > 0:
+        errs.pop('tor_numel')
+    return errs
+
+
+# ---------------------------------------------------------------------------------------------- golden fixtures
+import os as _os
+
+GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), 'golden')
+
+
+def load_golden(name):
+    return torch.load(_os.path.join(GOLDEN, name), weights_only=False)
+
+
+def golden_model(case, which):
+    """Model ('oracle' on CPU | 'product' on cuda:0) + pose list rebuilt from a ref_cg_model.pt case."""
+    from argparse import Namespace
+    from functools import partial
+    from diffdock_b200.hetero import graph_from_dict
+    a = Namespace(**case['args'])
+    if which == 'oracle':
+        from oracle.cg_model import CGModel
+        from oracle.layers import get_timestep_embedding
+        from oracle.diffusion import t_to_sigma
+        dev = 'cpu'
+    else:
+        from diffdock_b200.cg_model import CGModel
+        from diffdock_b200.diffusion_utils import get_timestep_embedding, t_to_sigma
+        dev = torch.device('cuda:0')
+    m = CGModel(partial(t_to_sigma, args=a), dev, get_timestep_embedding('sinusoidal', 8, a.embedding_scale),
+                **case['kw']).eval()
+    if case['lm_dim']:   # the fixture shrinks the 1280-wide LM embedding to 16 columns (see make_golden.py)
+        m.rec_node_embedding.additional_features_dim = case['lm_dim']
+        m.rec_node_embedding.additional_features_embedder = torch.nn.Linear(case['lm_dim'] + 6, 6)
+    m.load_state_dict(case['state'], strict=True)
+    poses = [graph_from_dict(d) for d in case['poses']]
+    return m.to(dev), poses, a
