@@ -24,6 +24,26 @@ def _need_cuda(*ts):
             raise RuntimeError("diffdock_b200 ops run on CUDA tensors only (no CPU fallback)")
 
 
+class _Profile:
+    """Optional live accounting used by bench.py: CUDA-event pairs around every tensor-product conv launch (on the
+    launching stream) with that launch's ALGORITHMIC bytes, and a count of all kernels
+    launched through this module."""
+
+    def __init__(self):
+        self.reset(False)
+
+    def reset(self, enabled=False):
+        self.enabled, self.pairs, self.bytes, self.all_launches = enabled, [], 0, 0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {'launches': len(self.pairs), 'ms': sum(a.elapsed_time(b) for a, b in self.pairs), 'bytes': self.bytes,
+                'all_launches': self.all_launches}
+
+
+PROFILE = _Profile()
+
+
 class TpHandle:
     """Device-resident tensor-product table (ddb200_tp_table)."""
 
@@ -53,7 +73,8 @@ class TpHandle:
             pass
 
 
-def tpconv_accumulate(h: TpHandle, x, edge_src, edge_dst, geo, w, sum_buf, cnt_buf=None, edge_weight=None):
+def tpconv_accumulate(h: TpHandle, x, edge_src, edge_dst, geo, w, sum_buf, cnt_buf=None, edge_weight=None,
+                      count_node_bytes=True):
     """sum_buf[edge_dst[e]] += TP(x[edge_src[e]], Y(geo[e]), w[e]) (* edge_weight[e]);  cnt_buf[edge_dst[e]] += 1."""
     _need_cuda(x, edge_src, edge_dst, geo, w, sum_buf)
     E = edge_src.shape[0]
@@ -69,9 +90,20 @@ def tpconv_accumulate(h: TpHandle, x, edge_src, edge_dst, geo, w, sum_buf, cnt_b
     if edge_weight is not None:
         edge_weight = edge_weight.reshape(-1).contiguous().float()
         assert edge_weight.shape[0] == E
+    prof = PROFILE.enabled
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _lib.lib().ddb200_tpconv_accumulate(h._h, _ptr(x), x.stride(0), _ptr(edge_src), _ptr(edge_dst), _ptr(geo),
                                              _ptr(edge_weight), _ptr(w), w.stride(0), E, _ptr(sum_buf), _ptr(cnt_buf),
                                              _stream())
+    if prof:
+        e1.record()
+        PROFILE.pairs.append((e0, e1))
+        PROFILE.bytes += E * (4 * t.weight_numel + 12 + 4) + (4 * E if edge_weight is not None else 0)
+        if count_node_bytes:   # node tensors are compulsory traffic once per (layer, edge set), not per edge block
+            PROFILE.bytes += 4 * (sum_buf.shape[0] + 1) + 4 * x.shape[0] * t.d_in + 4 * sum_buf.shape[0] * t.d_out
+        PROFILE.all_launches += 1
     _lib.check(rc, 'ddb200_tpconv_accumulate')
 
 
@@ -87,6 +119,7 @@ def tpconv_finalize(sum_buf, cnt_buf, mean, bn_scale=None, bn_shift=None, residu
     rc = _lib.lib().ddb200_tpconv_finalize(_ptr(sum_buf), _ptr(cnt_buf), n, d, 1 if mean else 0, _ptr(bn_scale),
                                            _ptr(bn_shift), _ptr(residual), res_stride, res_dim, _ptr(out), _stream())
     _lib.check(rc, 'ddb200_tpconv_finalize')
+    PROFILE.all_launches += 1
     return out
 
 
@@ -122,4 +155,25 @@ def radius(x, y, x_ptr, y_batch, r=1.0, r_per_graph=None, max_num_neighbors=32, 
                                   int(max_num_neighbors), int(exclude_self), _ptr(row_start), _ptr(row), _ptr(col),
                                   _stream())
         _lib.check(rc, 'ddb200_radius_fill')
+    PROFILE.all_launches += 2
     return row, col, count
+
+
+def pose_update(pos, n_poses, bond_u, bond_v, mask_rotate_u8, tr_score, rot_score, tor_score, coef, tr_z=None,
+                rot_z=None, tor_z=None, use_torsion=True):
+    """New ligand coordinates [n_poses * n_atoms, 3] after one reverse-diffusion step (ddb200_pose_update)."""
+    _need_cuda(pos, tr_score, rot_score)
+    pos = pos.float().contiguous()
+    n_atoms = pos.shape[0] // n_poses
+    n_bonds = int(bond_u.shape[0]) if bond_u is not None else 0
+    f = lambda t: t.float().contiguous() if t is not None else None
+    tr_score, rot_score, tor_score, tr_z, rot_z, tor_z = map(f, (tr_score, rot_score, tor_score, tr_z, rot_z, tor_z))
+    out = torch.empty_like(pos)
+    c = (C.c_float * 6)(*[float(v) for v in coef])
+    rc = _lib.lib().ddb200_pose_update(_ptr(pos), n_poses, n_atoms, n_bonds, _ptr(bond_u), _ptr(bond_v),
+                                       _ptr(mask_rotate_u8), _ptr(tr_score), _ptr(rot_score), _ptr(tor_score),
+                                       _ptr(tr_z), _ptr(rot_z), _ptr(tor_z), C.cast(c, C.c_void_p),
+                                       1 if use_torsion else 0, _ptr(out), _stream())
+    _lib.check(rc, 'ddb200_pose_update')
+    PROFILE.all_launches += 1
+    return out

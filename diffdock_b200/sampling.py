@@ -1,0 +1,149 @@
+"""Reverse-diffusion sampler: drop-in for ``utils/sampling.py:sampling`` (same arguments and return value).
+
+Per step the reference runs ~40 small PyTorch ops, a Python loop over rotatable bonds with host-sync asserts and a
+batched cuSOLVER SVD (utils/sampling.py:133-191, utils/diffusion_utils.py:60-78, utils/torsion.py:75-90,
+utils/geometry.py:246-276).  Here a step is: ``set_time`` (device fills) -> score model -> ONE pose-update kernel
+(``ddb200_pose_update``) that forms the three perturbations from host-computed SDE coefficients, moves the ligand
+rigidly, applies the torsion updates sequentially and Kabsch-aligns - no host synchronisation inside the loop apart
+from the neighbour-list sizes in the score model.
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .diffusion_utils import set_time
+from .hetero import collate
+
+
+def is_iterable(arr):
+    try:
+        iter(arr)
+        return True
+    except TypeError:
+        return False
+
+
+def _triple(v):
+    return list(v) if is_iterable(v) else [v] * 3
+
+
+def _nan_guard(tr, rot, tor):
+    """utils/sampling.py:117-131 without the host round trip: scores are only touched when a NaN shows up in the
+    per-pose mean of the translation score."""
+    cond = torch.isnan(tr.mean(dim=-1)).any()
+
+    def fix(s):
+        if s is None or s.numel() == 0:
+            return s
+        eps = 0.01 * torch.nanmean(s.abs())
+        s = torch.where(cond & torch.isnan(s), eps, s)
+        s = torch.where(cond & (s == float('inf')), eps, s)
+        return torch.where(cond & (s == float('-inf')), -eps, s)
+
+    return fix(tr), fix(rot), fix(tor)
+
+
+def step_coefficients(t_idx, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_to_sigma, model_args, ode,
+                      temp_sampling, temp_psi, temp_sigma_data):
+    """Host scalars (a, c) per degree of freedom such that  perturbation = a * score + c * z
+    (utils/sampling.py:97-102,133-186)."""
+    last = t_idx == inference_steps - 1
+    ts, tp, tsd = _triple(temp_sampling), _triple(temp_psi), _triple(temp_sigma_data)
+    out = []
+    sig = t_to_sigma(tr_schedule[t_idx], rot_schedule[t_idx], tor_schedule[t_idx])
+    lims = [(model_args.tr_sigma_min, model_args.tr_sigma_max), (model_args.rot_sigma_min, model_args.rot_sigma_max),
+            (model_args.tor_sigma_min, model_args.tor_sigma_max)]
+    for k, sched in enumerate((tr_schedule, rot_schedule, tor_schedule)):
+        dt = float(sched[t_idx] - sched[t_idx + 1]) if not last else float(sched[t_idx])
+        s_min, s_max = lims[k]
+        sigma = float(sig[k])
+        g = sigma * math.sqrt(2 * math.log(s_max / s_min))
+        if ode:
+            a, c = 0.5 * g * g * dt, 0.0
+        else:
+            a, c = g * g * dt, g * math.sqrt(dt)
+        if ts[k] != 1.0:       # low-temperature sampling, :173-186 (uses the SDE form even when ode is set)
+            sigma_data = math.exp(tsd[k] * math.log(s_max) + (1 - tsd[k]) * math.log(s_min))
+            lam = (sigma_data + sigma) / (sigma_data + sigma / ts[k])
+            a, c = g * g * dt * (lam + ts[k] * tp[k] / 2), g * math.sqrt(dt * (1 + tp[k]))
+        out += [a, c]
+    return out
+
+
+@torch.no_grad()
+def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
+             no_random=False, ode=False, visualization_list=None, confidence_model=None, confidence_data_list=None,
+             confidence_model_args=None, t_schedule=None, batch_size=32, no_final_step_noise=False, pivot=None,
+             return_full_trajectory=False, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5, return_features=False,
+             noise_fn=None):
+    """``noise_fn(kind, shape) -> tensor`` (kind in 'tr','rot','tor') replaces the device RNG when given - used by the
+    injected-noise parity tests; otherwise torch.normal is drawn on ``device`` in the reference's order."""
+    assert not (return_full_trajectory or return_features or pivot), "Not implemented yet in new inference version"
+    if getattr(model_args, 'crop_beyond', None) is not None:
+        raise NotImplementedError("crop_beyond (utils/utils.py:388-413) is not built yet - SURVEY.md row a19")
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError("diffdock_b200.sampling runs on a CUDA device only (no CPU fallback)")
+    N = len(data_list)
+    lig0 = data_list[0]['ligand']
+    mask_rotate = np.asarray(lig0.mask_rotate[0] if isinstance(lig0.mask_rotate, list) else lig0.mask_rotate)
+    mask_u8 = torch.from_numpy(mask_rotate.astype(np.uint8)).contiguous().to(device)
+    ei0 = data_list[0]['ligand', 'ligand'].edge_index
+    rot_bonds = ei0.T[lig0.edge_mask.cpu()] if ei0.numel() else ei0.T
+    bond_u = rot_bonds[:, 0].to(torch.int32).contiguous().to(device)
+    bond_v = rot_bonds[:, 1].to(torch.int32).contiguous().to(device)
+    use_torsion = not model_args.no_torsion
+    confidence = [] if confidence_model is not None else None
+    conf_batches = None
+    if confidence_model is not None and confidence_data_list is not None:
+        conf_batches = [confidence_data_list[i:i + batch_size] for i in range(0, len(confidence_data_list), batch_size)]
+
+    for batch_id, b0 in enumerate(range(0, N, batch_size)):
+        g = collate(data_list[b0:b0 + batch_size]).to(device, non_blocking=True)
+        b = g.num_graphs
+        n = len(g['ligand'].pos) // b
+        for t_idx in range(inference_steps):
+            t_tr, t_rot, t_tor = tr_schedule[t_idx], rot_schedule[t_idx], tor_schedule[t_idx]
+            coef = step_coefficients(t_idx, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_to_sigma,
+                                     model_args, ode, temp_sampling, temp_psi, temp_sigma_data)
+            set_time(g, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b,
+                     bool(getattr(model_args, 'all_atoms', False)), device)
+            tr_score, rot_score, tor_score = model(g)[:3]
+            tr_score, rot_score, tor_score = _nan_guard(tr_score, rot_score, tor_score)
+            zero = no_random or (no_final_step_noise and t_idx == inference_steps - 1)
+            tr_z = rot_z = tor_z = None
+            if not ode and not zero:
+                draw = (lambda kind, shape: noise_fn(kind, shape).to(device)) if noise_fn is not None else \
+                    (lambda kind, shape: torch.normal(mean=0, std=1, size=shape, device=device))
+                tr_z = draw('tr', (min(batch_size, N), 3))
+                rot_z = draw('rot', (min(batch_size, N), 3))
+                if use_torsion:
+                    tor_z = draw('tor', tuple(tor_score.shape))
+            g['ligand'].pos = ops.pose_update(g['ligand'].pos, b, bond_u, bond_v, mask_u8, tr_score, rot_score,
+                                              tor_score if use_torsion and tor_score.numel() else None, coef,
+                                              tr_z, rot_z, tor_z, use_torsion=use_torsion and tor_score.numel() > 0)
+            if visualization_list is not None:
+                for idx_b in range(b):
+                    visualization_list[batch_id * batch_size + idx_b].add(
+                        (g['ligand'].pos[idx_b * n:n * (idx_b + 1)].detach().cpu()
+                         + data_list[batch_id * batch_size + idx_b].original_center.detach().cpu()), part=1, order=t_idx + 2)
+        for i in range(b):
+            data_list[b0 + i]['ligand'].pos = g['ligand'].pos[i * n:n * (i + 1)]
+        if confidence_model is not None:
+            if conf_batches is not None:
+                cg = collate(copy.deepcopy(conf_batches[batch_id]))
+                cg['ligand'].pos = g['ligand'].pos.cpu()
+                cg = cg.to(device)
+                set_time(cg, 0, 0, 0, 0, b, confidence_model_args.all_atoms, device)
+                out = confidence_model(cg)
+            else:
+                out = confidence_model(g)
+            confidence.append(out[0] if type(out) is tuple else out)
+    if confidence_model is not None:
+        confidence = torch.nan_to_num(torch.cat(confidence, dim=0), nan=-1000)
+    return data_list, confidence

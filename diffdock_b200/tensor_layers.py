@@ -226,7 +226,7 @@ class TensorProductConvLayer(nn.Module):
                 if ew_scalar != 1.0:
                     w = w * ew_scalar
                 ops.tpconv_accumulate(handle, x, src32[b0:b1], tgt32[b0:b1], geo[b0:b1], w, sum_buf, cnt_buf,
-                                      edge_weight=ew[b0:b1] if ew is not None else None)
+                                      edge_weight=ew[b0:b1] if ew is not None else None, count_node_bytes=b0 == 0)
                 del w
             s = e
         res = x if self.residual else None

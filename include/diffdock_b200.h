@@ -98,6 +98,22 @@ int ddb200_radius_fill(const float* x, const float* y, const int32_t* x_ptr, con
                        const float* r_per_graph, float r, int64_t n_y, int max_neighbors, int exclude_self,
                        const int32_t* row_start, int32_t* out_row, int32_t* out_col, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * One reverse-diffusion pose update for n_poses copies of one ligand (n_atoms atoms, n_bonds rotatable bonds):
+ *   tr  = coef[0] * tr_score  + coef[1] * tr_z        rot = coef[2] * rot_score + coef[3] * rot_z
+ *   tor = coef[4] * tor_score + coef[5] * tor_z       (z pointers may be NULL = no noise; coef6 is a HOST array)
+ *   rigid move about the ligand centroid, sequential torsion rotations (bond_u/bond_v [n_bonds], mask_rotate
+ *   [n_bonds, n_atoms] bytes), Kabsch re-alignment of the flexed pose onto the rigid one.
+ * pos / out_pos [n_poses * n_atoms, 3]; tr/rot [n_poses, 3]; tor [n_poses * n_bonds].  use_torsion = 0 skips the
+ * torsion + Kabsch part (model_args.no_torsion).
+ * Replaces: utils/sampling.py:133-186 (perturbations), utils/diffusion_utils.py:60-78, utils/torsion.py:75-90,
+ * utils/geometry.py:72-86,246-276.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_pose_update(const float* pos, int64_t n_poses, int n_atoms, int n_bonds, const int32_t* bond_u,
+                       const int32_t* bond_v, const uint8_t* mask_rotate, const float* tr_score,
+                       const float* rot_score, const float* tor_score, const float* tr_z, const float* rot_z,
+                       const float* tor_z, const float* coef6, int use_torsion, float* out_pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
