@@ -54,6 +54,12 @@ def randomise_bn(model, seed):
                 m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
 
 
+def host_threads():
+    """Threads for the CPU oracle: every host core up to 32 (beyond that the oracle's many small PyTorch ops lose time
+    to oversubscription: 134 s/pose-step with 128 threads vs 17 s with 8 on this workload); override DDB200_CPU_THREADS."""
+    return int(os.environ.get('DDB200_CPU_THREADS', min(os.cpu_count() or 1, 32)))
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -64,12 +70,12 @@ def peaks():
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
         q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -77,10 +83,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(',')])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
@@ -124,7 +130,7 @@ def run_reference(cli):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     args = default_model_args(sh_lmax=cli.sh_lmax)
     step = oracle_step_fn(args, cli.n_res, cli.n_atoms, seed=100)
@@ -240,6 +246,12 @@ def run_cuda(cli):
     value = world * cli.poses / (N_SCHED * ms_max * 1e-3)
 
     # ---- end to end through the public API with host inputs ---------------------------------------------------
+    if cli.no_e2e:
+        if rank == 0:
+            print(json.dumps({"profiling_run": True, "ms_per_step": ms_max, "value": value, "tpconv": prof}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     host_list = [p.clone() for p in poses]
     for p in host_list:
         p._apply(lambda t: t.pin_memory() if t.is_floating_point() or t.dtype in (torch.int64, torch.bool) else t)
@@ -277,7 +289,7 @@ def run_cuda(cli):
                         "d2h_bytes_per_step": int(final.numel() * 4 // N_SCHED), "seconds_per_run": float(t_e.item())},
                 "gpu_launches": prof['all_launches'], "roofline": roof}
         if world == 1 and not cli.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = host_threads()
             torch.set_num_threads(cores)
             ostep = oracle_step_fn(args, cli.n_res, cli.n_atoms, seed=100)
             t0 = time.perf_counter()
@@ -303,6 +315,7 @@ def main():
     ap.add_argument('--n-atoms', dest='n_atoms', type=int, default=40)
     ap.add_argument('--sh-lmax', dest='sh_lmax', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
     cli = ap.parse_args()
     cli.warmup = max(cli.warmup, 0)
     if cli.impl == 'reference':

@@ -1,0 +1,48 @@
+"""Multi-GPU driver: poses / complexes are independent units, so each rank samples a contiguous
+block with no collective inside the step loop; ONE all_gather of the final ligand coordinates at the end
+(NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, rank: int, world: int):
+    """Contiguous, size-balanced block [lo, hi) of ``n_items`` for ``rank`` (first ``n_items % world`` ranks get one more)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_positions(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """local [n_local, n_atoms, 3] on every rank -> [n_total, n_atoms, 3] on every rank (shards may differ by one pose)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_max = (n_total + world - 1) // world
+    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    out = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, r, world)
+        out.append(bufs[r][:hi - lo])
+    return torch.cat(out, 0)
+
+
+def sample_sharded(data_list: Sequence, sampler: Callable[[List], List], group=None) -> torch.Tensor:
+    """Runs ``sampler(local_block)`` (e.g. a partial of diffdock_b200.sampling.sampling) on this rank's block of poses of
+    one complex and returns the final coordinates of ALL poses, [len(data_list), n_atoms, 3], on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(len(data_list), rank, world)
+    block = list(data_list[lo:hi])
+    done = sampler(block) if block else []
+    n_atoms = data_list[0]['ligand'].pos.shape[0]
+    ref = done[0]['ligand'].pos if done else data_list[0]['ligand'].pos
+    local = torch.stack([d['ligand'].pos for d in done]) if done else ref.new_zeros((0, n_atoms, 3))
+    if world == 1:
+        return local
+    return all_gather_positions(local, len(data_list), group)
