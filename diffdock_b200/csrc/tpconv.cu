@@ -26,7 +26,7 @@ constexpr int WARP = 32;
 constexpr int HDR = 32;
 constexpr int ERUN = 32;          // edges per work unit (one lane holds one edge's indices/geometry)
 constexpr int MAX_XREG = 8;       // register prefetch of the next source row covers D_in <= 256
-constexpr uint32_t MAGIC = 0x44423230u;
+constexpr uint32_t MAGIC = 0x44423231u;
 
 struct KParams {
   const float* x; long long x_stride;
@@ -74,28 +74,50 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   return p;
 }
 
-template <int DOUT>
-__device__ __forceinline__ void contract_tile(const float* __restrict__ wp, const float* __restrict__ zp, int rows,
-                                              int r, int R, int rs, float* __restrict__ acc_slot) {
-  float acc[DOUT];
+// ---- weight-tile contraction: acc[v*DOUT+k] += W[u, c*VEC+v] * z[u, k] over the rows u = r, r+R, ... of the tile ----
+// Lane (r, c) owns VEC consecutive output channels and every R-th row; W comes from the TMA stage with one
+// LDS.128/LDS.64 per row, z[u, :] with one LDS (DOUT=1) or one LDS.128 (DOUT=3, rows padded to 4 floats).
+template <int VEC, int DOUT>
+__device__ __forceinline__ void contract_vec(const float* __restrict__ wp, const float* __restrict__ zp, int nrows,
+                                             int r, int R, int rs, float* __restrict__ acc) {
+  constexpr int ZS = (DOUT == 1) ? 1 : 4;
+  const int wstep = R * rs, zstep = R * ZS;
+#pragma unroll 2
+  for (int u = r; u < nrows; u += R) {
+    float w[VEC], z[DOUT];
+    if constexpr (VEC == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(wp);
+      w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+    } else {
+      const float2 t = *reinterpret_cast<const float2*>(wp);
+      w[0] = t.x; w[1] = t.y;
+    }
+    if constexpr (DOUT == 1) {
+      z[0] = *zp;
+    } else {
+      const float4 t = *reinterpret_cast<const float4*>(zp);
+      z[0] = t.x; z[1] = t.y; z[2] = t.z;
+    }
 #pragma unroll
-  for (int k = 0; k < DOUT; ++k) acc[k] = 0.f;
-  const int wstep = R * rs, zstep = R * DOUT;
-  wp += r * rs;
-  zp += r * DOUT;
-#pragma unroll 4
-  for (int u = r; u < rows; u += R) {
-    const float wv = *wp;
+    for (int v = 0; v < VEC; ++v)
 #pragma unroll
-    for (int k = 0; k < DOUT; ++k) acc[k] = fmaf(wv, zp[k], acc[k]);
+      for (int k = 0; k < DOUT; ++k) acc[v * DOUT + k] = fmaf(w[v], z[k], acc[v * DOUT + k]);
     wp += wstep;
     zp += zstep;
   }
-#pragma unroll
-  for (int k = 0; k < DOUT; ++k) acc_slot[k * WARP] += acc[k];
 }
 
-__global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams p) {
+// generic fallback (any 2l+1 <= 9, scalar weight loads): second-order representations, odd multiplicities
+__device__ __noinline__ void contract_generic(const float* __restrict__ wp, const float* __restrict__ zp, int nrows,
+                                              int r, int R, int rs, int dout, int zs, float* __restrict__ acc) {
+  for (int u = r; u < nrows; u += R) {
+    const float wv = wp[(u - r) * rs];
+    const float* zz = zp + (u - r) * zs;
+    for (int k = 0; k < dout; ++k) acc[k] = fmaf(wv, zz[k], acc[k]);
+  }
+}
+
+__global__ void __launch_bounds__(512, 1) tpconv_accumulate_kernel(const KParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -122,17 +144,27 @@ __global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams
   const int* terms_y = tb + tb[19];
   const int* outmap = tb + tb[20];
 
+  // lane -> (row group r, column slot c) for the (at most four) lanes-per-row values the table uses
+  int lr[4], lc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int lpr = tb[22 + q] > 0 ? tb[22 + q] : 32;
+    lr[q] = lane / lpr;
+    lc[q] = lane - lr[q] * lpr;
+  }
+
   // ---- per-warp scratch ---------------------------------------------------------------------------------------
   float* wsm = warp_base + (size_t)warp * p.warp_floats;
   float* stage_base = wsm;                                     // stages * stage_floats
-  float* xs = stage_base + (size_t)p.stages * p.stage_floats;  // D_in
+  float* zs = stage_base + (size_t)p.stages * p.stage_floats;  // z_total (16-byte aligned rows)
+  float* racc = zs + ((z_total + 3) & ~3);                     // n_acc * 32
+  float* xs = racc + n_acc * WARP;                             // D_in
   float* ys = xs + ((D_in + 3) & ~3);                          // D_sh
   float* ms = ys + ((D_sh + 3) & ~3);                          // m_total
-  float* zs = ms + ((m_total + 3) & ~3);                       // z_total
-  float* racc = zs + ((z_total + 3) & ~3);                     // n_acc * 32
   uint64_t* mybar = bars + warp * p.stages;
   for (int i = lane; i < n_acc * WARP; i += WARP) racc[i] = 0.f;
   for (int i = lane; i < m_total; i += WARP) ms[i] = 0.f;   // structurally-zero CG entries are never rewritten
+  for (int i = lane; i < z_total; i += WARP) zs[i] = 0.f;   // padding lanes of z rows stay zero
   __syncwarp();
 
   const long long E = p.n_edges;
@@ -171,6 +203,20 @@ __global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams
   uint32_t c_par = 0;
   const int nxr = (D_in + WARP - 1) / WARP;
 
+  auto flush_row = [&](int row, int row_edges) {
+    __syncwarp();
+    float* srow = p.sum + (long long)row * D_out;
+    for (int o = lane; o < D_out; o += WARP) {
+      const int* om = outmap + 3 * o;
+      float v = 0.f;
+      for (int r = 0; r < om[2]; ++r) v += racc[om[0] + r * om[1]];
+      atomicAdd(srow + o, v);
+    }
+    if (p.cnt && lane == 0) atomicAdd(p.cnt + row, (float)row_edges);
+    __syncwarp();
+    for (int j = lane; j < n_acc * WARP; j += WARP) racc[j] = 0.f;
+  };
+
   for (long long unit = gw; unit < n_units; unit += TW) {
     const long long e0 = unit * ERUN;
     const int ne = (int)((E - e0) < ERUN ? (E - e0) : ERUN);
@@ -199,19 +245,7 @@ __global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams
       const int src = __shfl_sync(0xffffffffu, l_src, i);
       const float ewt = __shfl_sync(0xffffffffu, l_ew, i);
       if (dst != cur_row) {
-        if (cur_row >= 0) {
-          __syncwarp();
-          float* srow = p.sum + (long long)cur_row * D_out;
-          for (int o = lane; o < D_out; o += WARP) {
-            const int* om = outmap + 3 * o;
-            float v = 0.f;
-            for (int r = 0; r < om[2]; ++r) v += racc[om[0] + r * om[1]];
-            atomicAdd(srow + o, v);
-          }
-          if (p.cnt && lane == 0) atomicAdd(p.cnt + cur_row, (float)row_edges);
-          __syncwarp();
-          for (int j = lane; j < n_acc * WARP; j += WARP) racc[j] = 0.f;
-        }
+        if (cur_row >= 0) flush_row(cur_row, row_edges);
         cur_row = dst;
         row_edges = 0;
       }
@@ -260,17 +294,45 @@ __global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams
       __syncwarp();
       // ---- z[u,k] = sum_i x[u,i] * M[i,k] -----------------------------------------------------------------------
       for (int q = 0; q < n_paths; ++q) {
-        const int* pa = paths + 6 * q;
-        const int in_off = pa[0], mul_in = pa[1], din = pa[2], dout = pa[3];
+        const int* pa = paths + 8 * q;
+        const int mul_in = pa[1];
+        const float* xp = xs + pa[0];
         const float* mp = ms + pa[5];
         float* zp = zs + pa[4];
-        const int n = mul_in * dout;
-        for (int idx = lane; idx < n; idx += WARP) {
-          const int u = idx / dout, k = idx - u * dout;
-          const float* xp = xs + in_off + u * din;
-          float a = 0.f;
-          for (int ii = 0; ii < din; ++ii) a = fmaf(xp[ii], mp[ii * dout + k], a);
-          zp[idx] = a;
+        switch (pa[7]) {
+          case 1:   // 0 x l -> 0 : z[u] = x[u] M
+            for (int u = lane; u < mul_in; u += WARP) zp[u] = xp[u] * mp[0];
+            break;
+          case 2: { // scalar in, vector out: z[u,:] = x[u] M[0,:]
+            const float m0 = mp[0], m1 = mp[1], m2 = mp[2];
+            for (int u = lane; u < mul_in; u += WARP) {
+              const float xv = xp[u];
+              *reinterpret_cast<float4*>(zp + 4 * u) = make_float4(xv * m0, xv * m1, xv * m2, 0.f);
+            }
+          } break;
+          case 3: { // vector in, scalar out: z[u] = x[u,:] . M[:,0]
+            const float m0 = mp[0], m1 = mp[1], m2 = mp[2];
+            for (int u = lane; u < mul_in; u += WARP)
+              zp[u] = fmaf(xp[3 * u], m0, fmaf(xp[3 * u + 1], m1, xp[3 * u + 2] * m2));
+          } break;
+          case 4: { // vector in, vector out: z[u,:] = x[u,:] M (3x3)
+            for (int u = lane; u < mul_in; u += WARP) {
+              const float x0 = xp[3 * u], x1 = xp[3 * u + 1], x2 = xp[3 * u + 2];
+              *reinterpret_cast<float4*>(zp + 4 * u) =
+                  make_float4(fmaf(x0, mp[0], fmaf(x1, mp[3], x2 * mp[6])), fmaf(x0, mp[1], fmaf(x1, mp[4], x2 * mp[7])),
+                              fmaf(x0, mp[2], fmaf(x1, mp[5], x2 * mp[8])), 0.f);
+            }
+          } break;
+          default: {
+            const int din = pa[2], dout = pa[3], zstr = pa[6];
+            const int n = mul_in * dout;
+            for (int idx = lane; idx < n; idx += WARP) {
+              const int u = idx / dout, k = idx - u * dout;
+              float a = 0.f;
+              for (int ii = 0; ii < din; ++ii) a = fmaf(xp[u * din + ii], mp[ii * dout + k], a);
+              zp[u * zstr + k] = a;
+            }
+          }
         }
       }
       __syncwarp();
@@ -282,26 +344,46 @@ __global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams
         for (int j = 0; j < MAX_XREG; ++j)
           xr[j] = (j < nxr && lane + WARP * j < D_in) ? __ldg(xrow + lane + WARP * j) : 0.f;
       }
-      // ---- weight contraction, chunk by chunk ------------------------------------------------------------------
+      // ---- weight contraction, chunk by chunk; accumulators persist over tiles of one output irrep -----------------
+      float acc[12];
       for (int c = 0; c < n_chunks; ++c) {
         const int* ch = chunks + 4 * c;
         while (!mbar_try_wait(&mybar[c_stage], c_par)) {}
         const float* st = stage_base + (size_t)c_stage * p.stage_floats;
         for (int t = ch[0]; t < ch[1]; ++t) {
-          const int* ti = tiles + 8 * t;
-          const int width = ti[5], R = ti[6];
-          const int r = lane / width, wl = lane - r * width;
+          const int* ti = tiles + 12 * t;
+          const int vec = ti[5], R = ti[7], flags = ti[9], kind = ti[11];
+          const int li = ti[6];
+          const int r = li == 0 ? lr[0] : (li == 1 ? lr[1] : (li == 2 ? lr[2] : lr[3]));
+          const int cc = li == 0 ? lc[0] : (li == 1 ? lc[1] : (li == 2 ? lc[2] : lc[3]));
+          if (flags & 1) {
+#pragma unroll
+            for (int q = 0; q < 12; ++q) acc[q] = 0.f;
+          }
           if (r < R) {
-            const float* wp = st + ti[0] + wl;
-            const float* zp = zs + ti[3];
-            float* as = racc + ti[7] + lane;
-            switch (ti[4]) {
-              case 1: contract_tile<1>(wp, zp, ti[2], r, R, ti[1], as); break;
-              case 3: contract_tile<3>(wp, zp, ti[2], r, R, ti[1], as); break;
-              case 5: contract_tile<5>(wp, zp, ti[2], r, R, ti[1], as); break;
-              case 7: contract_tile<7>(wp, zp, ti[2], r, R, ti[1], as); break;
-              default: contract_tile<9>(wp, zp, ti[2], r, R, ti[1], as); break;
+            const float* wp = st + ti[0] + r * ti[1] + cc * vec;
+            const float* zp = zs + ti[3] + r * ti[10];
+            switch (kind) {
+              case 1: contract_vec<4, 1>(wp, zp, ti[2], r, R, ti[1], acc); break;
+              case 2: contract_vec<4, 3>(wp, zp, ti[2], r, R, ti[1], acc); break;
+              case 3: contract_vec<2, 1>(wp, zp, ti[2], r, R, ti[1], acc); break;
+              case 4: contract_vec<2, 3>(wp, zp, ti[2], r, R, ti[1], acc); break;
+              default: {   // keep acc[] in registers: the out-of-line generic path works on a private copy
+                float tmp[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) tmp[q] = acc[q];
+                contract_generic(wp, zp, ti[2], r, R, ti[1], ti[4], ti[10], tmp);
+#pragma unroll
+                for (int q = 0; q < 9; ++q) acc[q] = tmp[q];
+              } break;
             }
+          }
+          if (flags & 2) {
+            float* as = racc + ti[8] + lane;
+            const int nq = vec * ti[4];
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+              if (q < nq) as[q * WARP] += acc[q];
           }
         }
         __syncwarp();
@@ -309,20 +391,7 @@ __global__ void __launch_bounds__(256, 1) tpconv_accumulate_kernel(const KParams
         if (++c_stage == p.stages) { c_stage = 0; c_par ^= 1u; }
       }
     }
-    // flush the last row of this run
-    if (cur_row >= 0) {
-      __syncwarp();
-      float* srow = p.sum + (long long)cur_row * D_out;
-      for (int o = lane; o < D_out; o += WARP) {
-        const int* om = outmap + 3 * o;
-        float v = 0.f;
-        for (int r = 0; r < om[2]; ++r) v += racc[om[0] + r * om[1]];
-        atomicAdd(srow + o, v);
-      }
-      if (p.cnt && lane == 0) atomicAdd(p.cnt + cur_row, (float)row_edges);
-      __syncwarp();
-      for (int j = lane; j < n_acc * WARP; j += WARP) racc[j] = 0.f;
-    }
+    if (cur_row >= 0) flush_row(cur_row, row_edges);   // last row of this run
   }
 }
 
@@ -363,10 +432,13 @@ static int plan_smem(ddb200_tp_table* t) {
   if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || max_smem <= 0)
     max_smem = 227 * 1024;
   const int shared_bytes = (al4(t->n_ints) + al4(t->n_terms)) * 4 + 256;
-  // prefer 8 warps x 2 stages; fall back to fewer warps, never fewer than 2 stages
-  for (int warps = 8; warps >= 1; --warps) {
-    for (int stages = 3; stages >= 2; --stages) {
-      if (warps == 8 && stages == 3) continue;  // 8x3 never fits next to the scratch for the full-width layer
+  // as many warps as fit (latency hiding), then as many ring stages as fit (bytes in flight), at least 2
+  static const int warp_opts[] = {16, 14, 12, 10, 8, 6, 4, 2, 1};
+  const char* env_w = getenv("DDB200_TPCONV_WARPS");
+  const char* env_s = getenv("DDB200_TPCONV_STAGES");
+  for (int warps : warp_opts) {
+    if (env_w && atoi(env_w) > 0 && warps > atoi(env_w)) continue;
+    for (int stages = (env_s && atoi(env_s) >= 2) ? atoi(env_s) : 4; stages >= 2; --stages) {
       const int wf = (stages * stage_floats + fixed + 31) & ~31;
       const long long need = (long long)shared_bytes + 8LL * (warps * stages + 2) + 128 + 4LL * wf * warps;
       if (need <= max_smem) {

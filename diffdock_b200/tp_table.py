@@ -27,7 +27,7 @@ import numpy as np
 
 from .irreps import irreps_dim, irreps_offsets, parse_irreps, real_cg
 
-MAGIC = 0x44423230  # 'DB20'
+MAGIC = 0x44423231  # 'DB21'
 HDR_INTS = 32
 WARP = 32
 
@@ -144,7 +144,7 @@ def _faster_paths(ins, shs, outs):
     return paths, off
 
 
-def build_table(in_irreps, sh_irreps, out_irreps, kind='fctp', sh_from_vector=True, stage_floats=2560) -> TpTable:
+def build_table(in_irreps, sh_irreps, out_irreps, kind='fctp', sh_from_vector=True, stage_floats=512) -> TpTable:
     ins, shs, outs = parse_irreps(in_irreps), parse_irreps(sh_irreps), parse_irreps(out_irreps)
     if kind == 'fctp':
         paths, numel = _fctp_paths(ins, shs, outs)
@@ -152,8 +152,9 @@ def build_table(in_irreps, sh_irreps, out_irreps, kind='fctp', sh_from_vector=Tr
         paths, numel = _faster_paths(ins, shs, outs)
     else:
         raise ValueError(kind)
-    # kernel layout: same block order, each block start rounded up to 4 floats (16 B, TMA bulk-copy alignment)
-    order = sorted(range(len(paths)), key=lambda i: paths[i].w_ref_off)
+    # kernel layout: blocks grouped by OUTPUT irrep (consecutive tiles then share register accumulators), reference
+    # order inside a group, each block start rounded up to 4 floats (16 B, TMA bulk-copy alignment)
+    order = sorted(range(len(paths)), key=lambda i: (paths[i].i_out, paths[i].w_ref_off))
     off = 0
     for i in order:
         off = _align4(off)
@@ -174,24 +175,47 @@ def build_table(in_irreps, sh_irreps, out_irreps, kind='fctp', sh_from_vector=Tr
     return t
 
 
+# tile kinds of the contraction loop (csrc/tpconv.cu): (vector width of the weight loads, 2 l_out + 1)
+_TILE_KIND = {(4, 1): 1, (4, 3): 2, (2, 1): 3, (2, 3): 4}
+# z kinds: (2 l_in + 1, 2 l_out + 1) with a specialised z[u,k] = sum_i x[u,i] M[i,k] loop
+_Z_KIND = {(1, 1): 1, (1, 3): 2, (3, 1): 3, (3, 3): 4}
+
+
 def _compile(t: TpTable, stage_floats: int):
     paths = t.paths
-    # z / M scratch offsets
-    z_off, m_off, zo, mo = [], [], 0, 0
-    for p in paths:
-        z_off.append(zo)
-        m_off.append(mo)
-        zo += p.mul_in * (2 * p.l_out + 1)
-        mo += (2 * p.l_in + 1) * (2 * p.l_out + 1)
-    # accumulator rows: one block of d_out rows (32 lanes each) per (out irrep, column tile of <=32 channels)
-    acc_base, n_acc = {}, 0
+    order = sorted(range(len(paths)), key=lambda i: paths[i].w_off)      # kernel (= weight-row) order
+    # z / M scratch: z rows are padded to 4 floats when d_out == 3 (one LDS.128 per row)
+    z_off, m_off, z_str = {}, {}, {}
+    zo = mo = 0
+    for pi in order:
+        p = paths[pi]
+        d_out = 2 * p.l_out + 1
+        z_str[pi] = 1 if d_out == 1 else (4 if d_out == 3 else d_out)
+        z_off[pi], m_off[pi] = zo, mo
+        zo = _align4(zo + p.mul_in * z_str[pi])
+        mo += (2 * p.l_in + 1) * d_out
+    # per output irrep: vector width, lanes per row, column tiles, accumulator rows
+    out_cfg, n_acc, lpr_list = {}, 0, []
     for c, (m3, l3, _) in enumerate(t.out_irreps):
-        for tile in range((m3 + WARP - 1) // WARP):
-            acc_base[(c, tile)] = n_acc
-            n_acc += 2 * l3 + 1
+        d = 2 * l3 + 1
+        vec = 4 if m3 % 4 == 0 else (2 if m3 % 2 == 0 else 1)
+        if (vec, d) not in _TILE_KIND:
+            vec = 1
+        cols_per_tile = min(m3, WARP * vec)
+        tiles_c = []
+        for c0 in range(0, m3, cols_per_tile):
+            ncol = min(cols_per_tile, m3 - c0)
+            lpr = ncol // vec
+            if lpr not in lpr_list:
+                lpr_list.append(lpr)
+            tiles_c.append((c0, ncol, lpr, n_acc))
+            n_acc += vec * d
+        out_cfg[c] = (vec, d, tiles_c)
+    assert len(lpr_list) <= 4, "more than 4 distinct lane-per-row values"
     # M entries and their CG terms
     ment, terms_y, terms_v = [], [], []
-    for pi, p in enumerate(paths):
+    for pi in order:
+        p = paths[pi]
         C = real_cg(p.l_in, p.l_sh, p.l_out)
         for i in range(2 * p.l_in + 1):
             for k in range(2 * p.l_out + 1):
@@ -202,60 +226,63 @@ def _compile(t: TpTable, stage_floats: int):
                 for j in js:
                     terms_y.append(p.sh_off + j)
                     terms_v.append(p.coef * C[i, j, k])
-    # weight tiles, grouped into TMA chunks of <= stage_floats contiguous floats
-    stage_floats = max(_align4(stage_floats), _align4(max((p.mul_out for p in paths), default=4)))
-    order = sorted(range(len(paths)), key=lambda i: paths[i].w_off)
-    tiles, chunks = [], []
+    # weight tiles (row pieces of path blocks) grouped into TMA chunks of <= stage_floats contiguous floats
+    stage_floats = max(_align4(stage_floats), _align4(2 * max((p.mul_out for p in paths), default=4)))
+    tiles, chunks, groups = [], [], []
     cur = None   # [tile_begin, g_off, n_floats]
     for pi in order:
         p = paths[pi]
-        d_out = 2 * p.l_out + 1
-        rows_per_piece = max(1, stage_floats // p.mul_out)
+        vec, d_out, tiles_c = out_cfg[p.i_out]
+        m = p.mul_out
+        rows_per_piece = max(1, stage_floats // m)
         u = 0
         while u < p.mul_in:
-            # keep sub-block starts 16-byte aligned: whole blocks, or row counts that keep (rows*mul_out) % 4 == 0
             nrow = min(rows_per_piece, p.mul_in - u)
-            if u + nrow < p.mul_in:
-                while nrow > 1 and (nrow * p.mul_out) % 4:
+            if u + nrow < p.mul_in:           # interior cut: keep the next piece 16-byte aligned
+                while nrow > 1 and (nrow * m) % 4:
                     nrow -= 1
-                assert (nrow * p.mul_out) % 4 == 0, "cannot split weight block on a 16-byte boundary"
-            g0 = p.w_off + u * p.mul_out
-            nfl = nrow * p.mul_out
-            end_aligned = _align4(g0 + nfl)
+                assert (nrow * m) % 4 == 0, "cannot split weight block on a 16-byte boundary"
+            g0 = p.w_off + u * m
+            end_aligned = _align4(g0 + nrow * m)
             if cur is None or cur[1] + cur[2] != g0 or (end_aligned - cur[1]) > stage_floats:
                 if cur is not None:
-                    chunks.append((cur[0], len(tiles), cur[1], _align4(cur[2])))
+                    chunks.append((cur[0], len(tiles), cur[1], cur[2]))
                 cur = [len(tiles), g0, 0]
             wloc0 = g0 - cur[1]
-            for c0 in range(0, p.mul_out, WARP):
-                width = min(WARP, p.mul_out - c0)
-                tiles.append((wloc0 + c0, p.mul_out, nrow, z_off[pi] + u * d_out, d_out, width, WARP // width,
-                              acc_base[(p.i_out, c0 // WARP)] * WARP))
+            for (c0, ncol, lpr, acc_row) in tiles_c:
+                kind = _TILE_KIND.get((vec, d_out), 0)
+                tiles.append([wloc0 + c0, m, nrow, z_off[pi] + u * z_str[pi], d_out, vec, lpr_list.index(lpr),
+                              WARP // lpr, acc_row * WARP, 0, z_str[pi], kind])
+                groups.append((p.i_out, c0) if len(tiles_c) == 1 else ('solo', len(tiles)))
             cur[2] = end_aligned - cur[1]
             u += nrow
     if cur is not None:
-        chunks.append((cur[0], len(tiles), cur[1], _align4(cur[2])))
+        chunks.append((cur[0], len(tiles), cur[1], cur[2]))
+    for i, tl in enumerate(tiles):     # first / last tile of a run that accumulates into the same registers
+        first = i == 0 or groups[i - 1] != groups[i]
+        last = i == len(tiles) - 1 or groups[i + 1] != groups[i]
+        tl[9] = (1 if first else 0) | (2 if last else 0)
     for (_, _, g, n) in chunks:
         assert g % 4 == 0 and n % 4 == 0 and n <= stage_floats and g + n <= t.weight_numel_padded
     # output map: out column -> (first accumulator slot, lane stride between row groups, #row groups)
     outmap = []
-    out_off = irreps_offsets(t.out_irreps)
     for c, (m3, l3, _) in enumerate(t.out_irreps):
-        d = 2 * l3 + 1
+        vec, d, tiles_c = out_cfg[c]
         for w in range(m3):
-            tile, wl = divmod(w, WARP)
-            width = min(WARP, m3 - tile * WARP)
+            c0, ncol, lpr, acc_row = next(tc for tc in tiles_c if tc[0] <= w < tc[0] + tc[1])
+            cl, v = divmod(w - c0, vec)
             for k in range(d):
-                outmap.append(((acc_base[(c, tile)] + k) * WARP + wl, width, WARP // width))
+                outmap.append(((acc_row + v * d + k) * WARP + cl, lpr, WARP // lpr))
     assert len(outmap) == t.d_out
 
     def sect(rows, ncol):
-        a = np.asarray(rows, dtype=np.int32).reshape(-1, ncol) if rows else np.zeros((0, ncol), np.int32)
+        a = np.asarray(rows, dtype=np.int32).reshape(-1, ncol) if len(rows) else np.zeros((0, ncol), np.int32)
         return a.reshape(-1)
 
-    s_paths = sect([(p.in_off, p.mul_in, 2 * p.l_in + 1, 2 * p.l_out + 1, z_off[i], m_off[i])
-                    for i, p in enumerate(paths)], 6)
-    s_tiles, s_chunks, s_ment = sect(tiles, 8), sect(chunks, 4), sect(ment, 3)
+    s_paths = sect([(paths[pi].in_off, paths[pi].mul_in, 2 * paths[pi].l_in + 1, 2 * paths[pi].l_out + 1, z_off[pi],
+                     m_off[pi], z_str[pi], _Z_KIND.get((2 * paths[pi].l_in + 1, 2 * paths[pi].l_out + 1), 0))
+                    for pi in order], 8)
+    s_tiles, s_chunks, s_ment = sect(tiles, 12), sect(chunks, 4), sect(ment, 3)
     s_ty, s_out = np.asarray(terms_y, dtype=np.int32), sect(outmap, 3)
     hdr = np.zeros(HDR_INTS, dtype=np.int32)
     offs, o = [], HDR_INTS
@@ -263,9 +290,10 @@ def _compile(t: TpTable, stage_floats: int):
         offs.append(o)
         o += len(s)
     hdr[:15] = [MAGIC, len(paths), len(tiles), len(chunks), len(ment), len(terms_y), t.d_in, t.d_sh, t.d_out,
-                t.sh_lmax, zo, mo, n_acc, t.weight_numel_padded, stage_floats]
+                t.sh_lmax, max(zo, 4), max(mo, 1), n_acc, t.weight_numel_padded, stage_floats]
     hdr[15:21] = offs
     hdr[21] = o
+    hdr[22:22 + len(lpr_list)] = lpr_list
     t.iblob = np.concatenate([hdr, s_paths, s_tiles, s_chunks, s_ment, s_ty, s_out]).astype(np.int32)
     t.fblob = np.asarray(terms_v if terms_v else [0.0], dtype=np.float32)
     t.stage_floats, t.n_chunks = stage_floats, len(chunks)
@@ -289,14 +317,15 @@ def spherical_harmonics_np(vec, lmax):
 
 
 def evaluate(t: TpTable, x, sh_or_vec, w_padded, edge_weight=None):
-    """Numpy interpreter of the compiled blobs: per-edge tensor-product messages [E, D_out] (float64).
-    ``w_padded`` is in the kernel layout ([E, weight_numel_padded])."""
+    """Numpy interpreter of the compiled blobs, lane by lane like the kernel: per-edge tensor-product messages
+    [E, D_out] (float64).  ``w_padded`` is in the kernel layout ([E, weight_numel_padded])."""
     ib, fb = t.iblob, t.fblob.astype(np.float64)
     (_, n_paths, n_tiles, n_chunks, n_ment, n_terms, d_in, d_sh, d_out, lmax, z_tot, m_tot, n_acc, wpad,
      _cap) = ib[:15]
     o_paths, o_tiles, o_chunks, o_ment, o_ty, o_out = ib[15:21]
-    paths = ib[o_paths:o_paths + 6 * n_paths].reshape(-1, 6)
-    tiles = ib[o_tiles:o_tiles + 8 * n_tiles].reshape(-1, 8)
+    lprs = ib[22:26]
+    paths = ib[o_paths:o_paths + 8 * n_paths].reshape(-1, 8)
+    tiles = ib[o_tiles:o_tiles + 12 * n_tiles].reshape(-1, 12)
     chunks = ib[o_chunks:o_chunks + 4 * n_chunks].reshape(-1, 4)
     ment = ib[o_ment:o_ment + 3 * n_ment].reshape(-1, 3)
     ty = ib[o_ty:o_ty + n_terms]
@@ -308,25 +337,36 @@ def evaluate(t: TpTable, x, sh_or_vec, w_padded, edge_weight=None):
     ew = np.ones(E) if edge_weight is None else np.asarray(edge_weight, np.float64).reshape(E)
     out = np.zeros((E, d_out))
     for e in range(E):
-        M = np.zeros(max(m_tot, 1))
+        M = np.zeros(m_tot)
         for (mi, tb, tc) in ment:
             M[mi] = ew[e] * sum(fb[q] * Y[e, ty[q]] for q in range(tb, tb + tc))
-        z = np.zeros(max(z_tot, 1))
-        for (in_off, mul_in, din, dout, zo, mo) in paths:
+        z = np.zeros(z_tot)
+        for (in_off, mul_in, din, dout, zo, mo, zs, _zk) in paths:
             xb = x[e, in_off:in_off + mul_in * din].reshape(mul_in, din)
-            z[zo:zo + mul_in * dout] = (xb @ M[mo:mo + din * dout].reshape(din, dout)).reshape(-1)
+            zz = xb @ M[mo:mo + din * dout].reshape(din, dout)
+            for u in range(mul_in):
+                z[zo + u * zs:zo + u * zs + dout] = zz[u]
         racc = np.zeros(n_acc * WARP)
+        acc = np.zeros((WARP, 12))
         for (tb, te, g_off, nfl) in chunks:
             stage = w[e, g_off:g_off + nfl]
-            for (wloc, rs, ucnt, zb, dout, width, R, ab) in tiles[tb:te]:
+            for (wloc, rs, nrows, zb, dout, vec, lpi, R, ab, flags, zs, _kind) in tiles[tb:te]:
+                lpr = lprs[lpi]
+                if flags & 1:
+                    acc[:] = 0
                 for lane in range(WARP):
-                    r, wl = divmod(lane, width)
+                    r, c = divmod(lane, lpr)
                     if r >= R:
                         continue
-                    for u in range(r, ucnt, R):
-                        wv = stage[wloc + u * rs + wl]
-                        for k in range(dout):
-                            racc[ab + k * WARP + lane] += wv * z[zb + u * dout + k]
+                    for u in range(r, nrows, R):
+                        for v in range(vec):
+                            wv = stage[wloc + u * rs + c * vec + v]
+                            for k in range(dout):
+                                acc[lane, v * dout + k] += wv * z[zb + u * zs + k]
+                if flags & 2:
+                    for lane in range(WARP):
+                        for q in range(vec * dout):
+                            racc[ab + q * WARP + lane] += acc[lane, q]
         for o, (base, stride, R) in enumerate(outmap):
             out[e, o] = sum(racc[base + r * stride] for r in range(R))
     return out

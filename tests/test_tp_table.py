@@ -36,7 +36,7 @@ def test_tables_match_oracle_tensor_products(i):
     for kind, shs, lmax in (('fctp', '1x0e+1x1o+1x2e', 2), ('faster', '1x0e+1x1o', 1), ('fctp', '1x0e+1x1o', 1)):
         err, t = _case(a, shs, b, kind, lmax)
         assert err < 1e-6
-        assert t.identity_layout and t.weight_numel % 4 == 0
+        assert t.weight_numel_padded % 4 == 0 and sorted(t.w_perm[t.w_perm >= 0]) == list(range(t.weight_numel))
 
 
 def test_weight_numel_table_of_survey_appendix_b():
@@ -58,7 +58,7 @@ def test_heads_second_order_and_padding():
     assert _case(seq[3], '1x0e+1x1o+1x2e', '2x1o + 2x1e', 'fctp', 2)[0] < 1e-6
     seq5 = get_irrep_seq(5, 3, True, True)                     # odd multiplicities -> padded weight rows
     err, t = _case(seq5[3], '1x0e+1x1o+1x2e', seq5[3], 'fctp', 2)
-    assert err < 1e-6 and not t.identity_layout and t.weight_numel_padded % 4 == 0
+    assert err < 1e-6 and t.weight_numel_padded > t.weight_numel and t.weight_numel_padded % 4 == 0
     T, tor_sh = full_tensor_product('1x0e+1x1o+1x2e', '1x2e')
     from diffdock_b200.irreps import irreps_str
     assert _case(seq[3], irreps_str(tor_sh), '48x0o + 48x0e', 'fctp', 2, given=True)[0] < 1e-6
@@ -74,9 +74,11 @@ def test_tma_chunks_are_aligned_and_cover_the_row():
     chunks = ib[ib[17]:ib[17] + 4 * ib[3]].reshape(-1, 4)
     covered = np.zeros(t.weight_numel_padded, dtype=int)
     for tb, te, g, n in chunks:
-        assert g % 4 == 0 and n % 4 == 0 and n <= ib[14] and te > tb
+        assert g % 4 == 0 and n % 4 == 0 and n <= ib[14] and te > tb      # 16-byte aligned TMA bulk copies
         covered[g:g + n] += 1
     assert np.all(covered == 1)
+    tiles = ib[ib[16]:ib[16] + 12 * ib[2]].reshape(-1, 12)
+    assert tiles[0][9] & 1 and tiles[-1][9] & 2                          # accumulator runs open and close
 
 
 def test_product_cg_blocks_equal_oracle_blocks():
