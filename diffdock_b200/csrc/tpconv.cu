@@ -26,7 +26,7 @@ constexpr int WARP = 32;
 constexpr int HDR = 32;
 constexpr int ERUN = 32;          // edges per work unit (one lane holds one edge's indices/geometry)
 constexpr int MAX_XREG = 8;       // register prefetch of the next source row covers D_in <= 256
-constexpr uint32_t MAGIC = 0x44423231u;
+constexpr uint32_t MAGIC = 0x44423232u;
 
 struct KParams {
   const float* x; long long x_stride;
@@ -39,6 +39,7 @@ struct KParams {
   int n_ints, n_terms;
   int stages, warps;
   int warp_floats;    // per-warp scratch size in floats
+  int warp_base_off;  // byte offset of the first warp's scratch inside dynamic shared memory
   int stage_floats;
 };
 
@@ -74,46 +75,52 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   return p;
 }
 
-// ---- weight-tile contraction: acc[v*DOUT+k] += W[u, c*VEC+v] * z[u, k] over the rows u = r, r+R, ... of the tile ----
+// ---- weight-tile contraction: acc[v*DOUT+k] += W[u, c*VEC+v] * z[u, k] over this lane's rows of the tile -----------
 // Lane (r, c) owns VEC consecutive output channels and every R-th row; W comes from the TMA stage with one
 // LDS.128/LDS.64 per row, z[u, :] with one LDS (DOUT=1) or one LDS.128 (DOUT=3, rows padded to 4 floats).
 template <int VEC, int DOUT>
-__device__ __forceinline__ void contract_vec(const float* __restrict__ wp, const float* __restrict__ zp, int nrows,
-                                             int r, int R, int rs, float* __restrict__ acc) {
-  constexpr int ZS = (DOUT == 1) ? 1 : 4;
-  const int wstep = R * rs, zstep = R * ZS;
-#pragma unroll 2
-  for (int u = r; u < nrows; u += R) {
-    float w[VEC], z[DOUT];
-    if constexpr (VEC == 4) {
-      const float4 t = *reinterpret_cast<const float4*>(wp);
-      w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
-    } else {
-      const float2 t = *reinterpret_cast<const float2*>(wp);
-      w[0] = t.x; w[1] = t.y;
-    }
-    if constexpr (DOUT == 1) {
-      z[0] = *zp;
-    } else {
-      const float4 t = *reinterpret_cast<const float4*>(zp);
-      z[0] = t.x; z[1] = t.y; z[2] = t.z;
-    }
-#pragma unroll
-    for (int v = 0; v < VEC; ++v)
-#pragma unroll
-      for (int k = 0; k < DOUT; ++k) acc[v * DOUT + k] = fmaf(w[v], z[k], acc[v * DOUT + k]);
-    wp += wstep;
-    zp += zstep;
+__device__ __forceinline__ void fma_row(const float* __restrict__ wp, const float* __restrict__ zp, float* __restrict__ acc) {
+  float w[VEC], z[DOUT];
+  if constexpr (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(wp);
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+  } else {
+    const float2 t = *reinterpret_cast<const float2*>(wp);
+    w[0] = t.x; w[1] = t.y;
   }
+  if constexpr (DOUT == 1) {
+    z[0] = *zp;
+  } else {
+    const float4 t = *reinterpret_cast<const float4*>(zp);
+    z[0] = t.x; z[1] = t.y; z[2] = t.z;
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int k = 0; k < DOUT; ++k) acc[v * DOUT + k] = fmaf(w[v], z[k], acc[v * DOUT + k]);
+}
+
+template <int VEC, int DOUT>
+__device__ __forceinline__ void run_rows(const float* __restrict__ wp, const float* __restrict__ zp, int n_it, int wstep,
+                                         int zstep, float* __restrict__ acc) {
+  int it = 0;
+  for (; it + 2 <= n_it; it += 2) {     // two independent rows in flight
+    fma_row<VEC, DOUT>(wp, zp, acc);
+    fma_row<VEC, DOUT>(wp + wstep, zp + zstep, acc);
+    wp += 2 * wstep;
+    zp += 2 * zstep;
+  }
+  if (it < n_it) fma_row<VEC, DOUT>(wp, zp, acc);
 }
 
 // generic fallback (any 2l+1 <= 9, scalar weight loads): second-order representations, odd multiplicities
-__device__ __noinline__ void contract_generic(const float* __restrict__ wp, const float* __restrict__ zp, int nrows,
-                                              int r, int R, int rs, int dout, int zs, float* __restrict__ acc) {
-  for (int u = r; u < nrows; u += R) {
-    const float wv = wp[(u - r) * rs];
-    const float* zz = zp + (u - r) * zs;
-    for (int k = 0; k < dout; ++k) acc[k] = fmaf(wv, zz[k], acc[k]);
+__device__ __noinline__ void run_rows_generic(const float* __restrict__ wp, const float* __restrict__ zp, int n_it,
+                                              int wstep, int zstep, int dout, float* __restrict__ acc) {
+  for (int it = 0; it < n_it; ++it) {
+    const float wv = *wp;
+    for (int k = 0; k < dout; ++k) acc[k] = fmaf(wv, zp[k], acc[k]);
+    wp += wstep;
+    zp += zstep;
   }
 }
 
@@ -127,8 +134,7 @@ __global__ void __launch_bounds__(512, 1) tpconv_accumulate_kernel(const KParams
   float* tval = reinterpret_cast<float*>(tb + ((p.n_ints + 3) & ~3));
   for (int i = threadIdx.x; i < p.n_terms; i += blockDim.x) tval[i] = p.fblob[i];
   uint64_t* bars = reinterpret_cast<uint64_t*>(tval + ((p.n_terms + 3) & ~3));
-  float* warp_base = reinterpret_cast<float*>(bars + ((p.warps * p.stages + 1) & ~1));
-  warp_base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(warp_base) + 127) & ~uintptr_t(127));
+  float* warp_base = reinterpret_cast<float*>(smem_raw + p.warp_base_off);   // offset planned on the host (128-B aligned)
   if (lane == 0)
     for (int s = 0; s < p.stages; ++s) mbar_init(&bars[warp * p.stages + s], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -344,51 +350,59 @@ __global__ void __launch_bounds__(512, 1) tpconv_accumulate_kernel(const KParams
         for (int j = 0; j < MAX_XREG; ++j)
           xr[j] = (j < nxr && lane + WARP * j < D_in) ? __ldg(xrow + lane + WARP * j) : 0.f;
       }
-      // ---- weight contraction, chunk by chunk; accumulators persist over tiles of one output irrep -----------------
-      float acc[12];
-      for (int c = 0; c < n_chunks; ++c) {
-        const int* ch = chunks + 4 * c;
-        while (!mbar_try_wait(&mybar[c_stage], c_par)) {}
-        const float* st = stage_base + (size_t)c_stage * p.stage_floats;
-        for (int t = ch[0]; t < ch[1]; ++t) {
-          const int* ti = tiles + 12 * t;
-          const int vec = ti[5], R = ti[7], flags = ti[9], kind = ti[11];
-          const int li = ti[6];
+      // ---- weight contraction: one accumulator run per output irrep, tiles = row pieces of the weight blocks --------
+      {
+        const int n_tiles = tb[2];
+        const int4* tiles4 = reinterpret_cast<const int4*>(tiles);
+        const float* st = stage_base;
+        int t = 0;
+        while (t < n_tiles) {
+          const int4 gb = tiles4[4 * t + 1], gc = tiles4[4 * t + 2];
+          const int rs = gb.x, dout = gb.y, vec = gb.z, li = gb.w, R = gc.x, accb = gc.y, zstr = gc.z, kind = gc.w;
           const int r = li == 0 ? lr[0] : (li == 1 ? lr[1] : (li == 2 ? lr[2] : lr[3]));
           const int cc = li == 0 ? lc[0] : (li == 1 ? lc[1] : (li == 2 ? lc[2] : lc[3]));
-          if (flags & 1) {
+          const bool active = r < R;
+          const int woff = r * rs + cc * vec, zoff = r * zstr, wstep = R * rs, zstep = R * zstr;
+          float acc[12];
 #pragma unroll
-            for (int q = 0; q < 12; ++q) acc[q] = 0.f;
-          }
-          if (r < R) {
-            const float* wp = st + ti[0] + r * ti[1] + cc * vec;
-            const float* zp = zs + ti[3] + r * ti[10];
+          for (int q = 0; q < 12; ++q) acc[q] = 0.f;
+          for (;;) {
+            const int4 ta = tiles4[4 * t];
+            if (ta.w & 4) {      // first tile of a TMA chunk: wait for its stage
+              while (!mbar_try_wait(&mybar[c_stage], c_par)) {}
+              st = stage_base + (size_t)c_stage * p.stage_floats;
+            }
+            const int n_it = active ? (ta.z & 0xffff) + (r < (ta.z >> 16) ? 1 : 0) : 0;
+            const float* wp = st + ta.x + woff;
+            const float* zp = zs + ta.y + zoff;
             switch (kind) {
-              case 1: contract_vec<4, 1>(wp, zp, ti[2], r, R, ti[1], acc); break;
-              case 2: contract_vec<4, 3>(wp, zp, ti[2], r, R, ti[1], acc); break;
-              case 3: contract_vec<2, 1>(wp, zp, ti[2], r, R, ti[1], acc); break;
-              case 4: contract_vec<2, 3>(wp, zp, ti[2], r, R, ti[1], acc); break;
+              case 1: run_rows<4, 1>(wp, zp, n_it, wstep, zstep, acc); break;
+              case 2: run_rows<4, 3>(wp, zp, n_it, wstep, zstep, acc); break;
+              case 3: run_rows<2, 1>(wp, zp, n_it, wstep, zstep, acc); break;
+              case 4: run_rows<2, 3>(wp, zp, n_it, wstep, zstep, acc); break;
               default: {   // keep acc[] in registers: the out-of-line generic path works on a private copy
                 float tmp[9];
 #pragma unroll
                 for (int q = 0; q < 9; ++q) tmp[q] = acc[q];
-                contract_generic(wp, zp, ti[2], r, R, ti[1], ti[4], ti[10], tmp);
+                run_rows_generic(wp, zp, n_it, wstep, zstep, dout, tmp);
 #pragma unroll
                 for (int q = 0; q < 9; ++q) acc[q] = tmp[q];
               } break;
             }
+            if (ta.w & 8) {      // last tile of the chunk: hand the stage back to the TMA producer
+              __syncwarp();
+              issue_next();
+              if (++c_stage == p.stages) { c_stage = 0; c_par ^= 1u; }
+            }
+            ++t;
+            if (ta.w & 2) break;
           }
-          if (flags & 2) {
-            float* as = racc + ti[8] + lane;
-            const int nq = vec * ti[4];
+          float* as = racc + accb + lane;
+          const int nq = vec * dout;
 #pragma unroll
-            for (int q = 0; q < 12; ++q)
-              if (q < nq) as[q * WARP] += acc[q];
-          }
+          for (int q = 0; q < 12; ++q)
+            if (q < nq) as[q * WARP] += acc[q];
         }
-        __syncwarp();
-        issue_next();   // refill the stage that was just drained
-        if (++c_stage == p.stages) { c_stage = 0; c_par ^= 1u; }
       }
     }
     if (cur_row >= 0) flush_row(cur_row, row_edges);   // last row of this run
@@ -419,7 +433,7 @@ struct ddb200_tp_table {
   float* d_fblob;
   int hdr[HDR];
   int n_ints, n_terms;
-  int warps, stages, warp_floats, smem_bytes;
+  int warps, stages, warp_floats, smem_bytes, warp_base_off;
 };
 
 static int plan_smem(ddb200_tp_table* t) {
@@ -440,9 +454,13 @@ static int plan_smem(ddb200_tp_table* t) {
     if (env_w && atoi(env_w) > 0 && warps > atoi(env_w)) continue;
     for (int stages = (env_s && atoi(env_s) >= 2) ? atoi(env_s) : 4; stages >= 2; --stages) {
       const int wf = (stages * stage_floats + fixed + 31) & ~31;
-      const long long need = (long long)shared_bytes + 8LL * (warps * stages + 2) + 128 + 4LL * wf * warps;
+      // [table ints | term values | mbarriers | (128-B aligned) per-warp scratch]
+      const long long bars_off = 4LL * (al4(t->n_ints) + al4(t->n_terms));
+      const long long base_off = (bars_off + 8LL * ((warps * stages + 1) & ~1) + 127) & ~127LL;
+      const long long need = base_off + 4LL * wf * warps;
       if (need <= max_smem) {
         t->warps = warps; t->stages = stages; t->warp_floats = wf; t->smem_bytes = (int)need;
+        t->warp_base_off = (int)base_off;
         return 0;
       }
     }
@@ -510,6 +528,7 @@ int ddb200_tpconv_accumulate(const ddb200_tp_table* t, const float* x, int64_t x
   p.w = w; p.w_stride = w_stride; p.n_edges = n_edges; p.sum = sum; p.cnt = cnt;
   p.iblob = t->d_iblob; p.fblob = t->d_fblob; p.n_ints = t->n_ints; p.n_terms = t->n_terms;
   p.stages = t->stages; p.warps = t->warps; p.warp_floats = t->warp_floats; p.stage_floats = t->hdr[14];
+  p.warp_base_off = t->warp_base_off;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

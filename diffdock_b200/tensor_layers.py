@@ -11,7 +11,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import ops
+from . import ops, radial
 from .irreps import irreps_dim, parse_irreps
 from .tp_table import build_table
 
@@ -134,6 +134,7 @@ class TensorProductConvLayer(nn.Module):
                                              dropout, activation) for _ in range(edge_groups)])
         self.batch_norm = IrrepsBatchNorm(out_irreps) if batch_norm else None
         self._wcache = {}
+        self._gcache = {}
 
     # -- radial MLP -> per-edge weights in kernel layout ------------------------------------------------------
     def _last_linear(self, fc, table):
@@ -154,9 +155,21 @@ class TensorProductConvLayer(nn.Module):
         return hit[1], hit[2]
 
     def _edge_weights(self, fc, table, edge_attr):
+        """Radial MLP -> per-edge tensor-product weights [E, >= weight_numel_padded] in the kernel's row layout.
+        The last (dominant) Linear runs on the tcgen05 tensor cores as a split-bf16 GEMM (csrc/radial_gemm.cu);
+        DDB200_RADIAL_GEMM=cublas selects the plain fp32 library GEMM instead."""
         h = edge_attr
         for m in list(fc)[:-1]:
             h = m(h)
+        if radial.USE_TENSOR_CORES and h.shape[1] <= radial.MAX_K and h.shape[0] >= 64:
+            lin = fc[-1]
+            key = (lin.weight._version, lin.bias._version, lin.weight.device)
+            hit = self._gcache.get(id(fc))
+            if hit is None or hit[0] != key:
+                W, b = self._last_linear(fc, table)
+                hit = (key,) + radial.build_b_images(W, b)
+                self._gcache[id(fc)] = hit
+            return radial.radial_gemm(h.contiguous(), hit[1], hit[2], hit[3])
         W, b = self._last_linear(fc, table)
         return F.linear(h, W, b)
 

@@ -27,7 +27,7 @@ import numpy as np
 
 from .irreps import irreps_dim, irreps_offsets, parse_irreps, real_cg
 
-MAGIC = 0x44423231  # 'DB21'
+MAGIC = 0x44423232  # 'DB22'
 HDR_INTS = 32
 WARP = 32
 
@@ -251,17 +251,23 @@ def _compile(t: TpTable, stage_floats: int):
             wloc0 = g0 - cur[1]
             for (c0, ncol, lpr, acc_row) in tiles_c:
                 kind = _TILE_KIND.get((vec, d_out), 0)
-                tiles.append([wloc0 + c0, m, nrow, z_off[pi] + u * z_str[pi], d_out, vec, lpr_list.index(lpr),
-                              WARP // lpr, acc_row * WARP, 0, z_str[pi], kind])
+                R = WARP // lpr
+                # record = 4 x int4: A (per-tile) | B, C (per accumulator run) | D
+                tiles.append([wloc0 + c0, z_off[pi] + u * z_str[pi], (nrow // R) | ((nrow % R) << 16), 0,
+                              m, d_out, vec, lpr_list.index(lpr),
+                              R, acc_row * WARP, z_str[pi], kind,
+                              nrow, 0, 0, 0])
                 groups.append((p.i_out, c0) if len(tiles_c) == 1 else ('solo', len(tiles)))
             cur[2] = end_aligned - cur[1]
             u += nrow
     if cur is not None:
         chunks.append((cur[0], len(tiles), cur[1], cur[2]))
+    chunk_first = {c[0] for c in chunks}
+    chunk_last = {c[1] - 1 for c in chunks}
     for i, tl in enumerate(tiles):     # first / last tile of a run that accumulates into the same registers
         first = i == 0 or groups[i - 1] != groups[i]
         last = i == len(tiles) - 1 or groups[i + 1] != groups[i]
-        tl[9] = (1 if first else 0) | (2 if last else 0)
+        tl[3] = (1 if first else 0) | (2 if last else 0) | (4 if i in chunk_first else 0) | (8 if i in chunk_last else 0)
     for (_, _, g, n) in chunks:
         assert g % 4 == 0 and n % 4 == 0 and n <= stage_floats and g + n <= t.weight_numel_padded
     # output map: out column -> (first accumulator slot, lane stride between row groups, #row groups)
@@ -282,7 +288,7 @@ def _compile(t: TpTable, stage_floats: int):
     s_paths = sect([(paths[pi].in_off, paths[pi].mul_in, 2 * paths[pi].l_in + 1, 2 * paths[pi].l_out + 1, z_off[pi],
                      m_off[pi], z_str[pi], _Z_KIND.get((2 * paths[pi].l_in + 1, 2 * paths[pi].l_out + 1), 0))
                     for pi in order], 8)
-    s_tiles, s_chunks, s_ment = sect(tiles, 12), sect(chunks, 4), sect(ment, 3)
+    s_tiles, s_chunks, s_ment = sect(tiles, 16), sect(chunks, 4), sect(ment, 3)
     s_ty, s_out = np.asarray(terms_y, dtype=np.int32), sect(outmap, 3)
     hdr = np.zeros(HDR_INTS, dtype=np.int32)
     offs, o = [], HDR_INTS
@@ -325,7 +331,7 @@ def evaluate(t: TpTable, x, sh_or_vec, w_padded, edge_weight=None):
     o_paths, o_tiles, o_chunks, o_ment, o_ty, o_out = ib[15:21]
     lprs = ib[22:26]
     paths = ib[o_paths:o_paths + 8 * n_paths].reshape(-1, 8)
-    tiles = ib[o_tiles:o_tiles + 12 * n_tiles].reshape(-1, 12)
+    tiles = ib[o_tiles:o_tiles + 16 * n_tiles].reshape(-1, 16)
     chunks = ib[o_chunks:o_chunks + 4 * n_chunks].reshape(-1, 4)
     ment = ib[o_ment:o_ment + 3 * n_ment].reshape(-1, 3)
     ty = ib[o_ty:o_ty + n_terms]
@@ -350,8 +356,9 @@ def evaluate(t: TpTable, x, sh_or_vec, w_padded, edge_weight=None):
         acc = np.zeros((WARP, 12))
         for (tb, te, g_off, nfl) in chunks:
             stage = w[e, g_off:g_off + nfl]
-            for (wloc, rs, nrows, zb, dout, vec, lpi, R, ab, flags, zs, _kind) in tiles[tb:te]:
+            for (wloc, zb, _nf, flags, rs, dout, vec, lpi, R, ab, zs, _kind, nrows, _a, _b, _c) in tiles[tb:te]:
                 lpr = lprs[lpi]
+                assert (_nf & 0xffff) == nrows // R and (_nf >> 16) == nrows % R
                 if flags & 1:
                     acc[:] = 0
                 for lane in range(WARP):

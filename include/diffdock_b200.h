@@ -114,6 +114,18 @@ int ddb200_pose_update(const float* pos, int64_t n_poses, int n_atoms, int n_bon
                        const float* rot_score, const float* tor_score, const float* tr_z, const float* rot_z,
                        const float* tor_z, const float* coef6, int use_torsion, float* out_pos, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Radial-MLP output layer on tcgen05 tensor cores:  out[e, n] = sum_k h[e, k] * W2[n, k] + bias[n], fp32-accurate
+ * through a split-bf16 (hi/lo) product evaluated as one bf16 GEMM over K' = 3K.
+ * h [n_edges, ldh] fp32 (K <= 149); b_images: bf16, [n_tiles_n][ceil(3K/64)][256 rows][64] pre-split
+ * ([hi | lo | hi] of W2 rows, zero padded) and 128B-swizzled shared-memory images built by
+ * diffdock_b200/radial.py:build_b_images (128-byte aligned); bias [n_tiles_n*256]; out [n_edges, ldo] fp32 with
+ * ldo >= n_tiles_n*256, ldo % 4 == 0, 16-byte aligned.  Columns are in the tensor-product table's weight-row layout.
+ * Replaces: the last nn.Linear of FCBlock (models/layers.py:16) applied at models/tensor_layers.py:140,211.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_radial_gemm(const float* h, int64_t ldh, int64_t n_edges, int K, const void* b_images, const float* bias,
+                       int n_tiles_n, float* out, int64_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

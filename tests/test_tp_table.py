@@ -77,8 +77,8 @@ def test_tma_chunks_are_aligned_and_cover_the_row():
         assert g % 4 == 0 and n % 4 == 0 and n <= ib[14] and te > tb      # 16-byte aligned TMA bulk copies
         covered[g:g + n] += 1
     assert np.all(covered == 1)
-    tiles = ib[ib[16]:ib[16] + 12 * ib[2]].reshape(-1, 12)
-    assert tiles[0][9] & 1 and tiles[-1][9] & 2                          # accumulator runs open and close
+    tiles = ib[ib[16]:ib[16] + 16 * ib[2]].reshape(-1, 16)
+    assert tiles[0][3] & 1 and tiles[-1][3] & 2                          # accumulator runs open and close
 
 
 def test_product_cg_blocks_equal_oracle_blocks():
