@@ -112,6 +112,53 @@ class HeteroGraph:
     def clone(self):
         return copy.deepcopy(self)
 
+    def to_data_list(self):
+        """Inverse of ``collate`` (torch_geometric Batch.to_data_list) for the attributes the path uses."""
+        B = self._globals['num_graphs']
+        ptr = {nt: st.ptr.tolist() if 'ptr' in st else None for nt, st in self._nodes.items()}
+        for nt, st in self._nodes.items():
+            if ptr[nt] is None:
+                cnt = torch.bincount(st.batch, minlength=B)
+                ptr[nt] = [0] + torch.cumsum(cnt, 0).tolist()
+        out = []
+        for b in range(B):
+            g = HeteroGraph()
+            for nt, st in self._nodes.items():
+                lo, hi = ptr[nt][b], ptr[nt][b + 1]
+                sl = st.__dict__.get('_slices', {})
+                for k, v in st.__dict__.items():
+                    if k in ('batch', 'ptr') or k.startswith('_'):
+                        continue
+                    if torch.is_tensor(v) and k in sl and sl[k][-1] == v.shape[0]:
+                        setattr(g[nt], k, v[sl[k][b]:sl[k][b + 1]])
+                    elif torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == ptr[nt][-1]:
+                        setattr(g[nt], k, v[lo:hi])
+                    elif isinstance(v, dict):
+                        setattr(g[nt], k, {a: t[lo:hi] for a, t in v.items()})
+                    elif isinstance(v, list) and len(v) == B:
+                        setattr(g[nt], k, v[b])
+            for et, st in self._edges.items():
+                ei = st.edge_index
+                src_ptr, dst_ptr = ptr[et[0]], ptr[et[1]]
+                sel = (ei[0] >= src_ptr[b]) & (ei[0] < src_ptr[b + 1])
+                for k, v in st.__dict__.items():
+                    if k == 'edge_index':
+                        off = torch.tensor([[src_ptr[b]], [dst_ptr[b]]], dtype=ei.dtype, device=ei.device)
+                        g[et].edge_index = ei[:, sel] - off
+                    elif torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == ei.shape[1]:
+                        setattr(g[et], k, v[sel])
+            for k, v in self._globals.items():
+                if k == 'num_graphs':
+                    continue
+                if isinstance(v, list) and len(v) == B:
+                    g._globals[k] = v[b]
+                elif torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B:
+                    g._globals[k] = v[b:b + 1]
+                elif isinstance(v, dict):
+                    g._globals[k] = {a: t[b:b + 1] for a, t in v.items()}
+            out.append(g)
+        return out
+
     def __deepcopy__(self, memo):
         g = HeteroGraph()
         for k, s in self._nodes.items():
@@ -140,12 +187,20 @@ def collate(data_list: List[HeteroGraph]) -> HeteroGraph:
             offs.append(offs[-1] + c)
         offsets[nt] = offs
         st = out[nt]
+        slices = {}
         for attr in data_list[0][nt].keys():
+            if attr.startswith('_'):
+                continue
             vals = [getattr(d[nt], attr) for d in data_list]
             if attr in _LIST_ATTRS or not torch.is_tensor(vals[0]):
                 setattr(st, attr, vals)
             else:
                 setattr(st, attr, torch.cat(vals, 0))
+                sizes = [0]
+                for v in vals:
+                    sizes.append(sizes[-1] + v.shape[0])
+                slices[attr] = sizes
+        st._slices = slices
         st.batch = torch.cat([torch.full((c,), i, dtype=torch.long) for i, c in enumerate(counts)])
         st.ptr = torch.tensor(offs, dtype=torch.long)
     for et in data_list[0].edge_types:

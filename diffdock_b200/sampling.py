@@ -75,6 +75,45 @@ def step_coefficients(t_idx, inference_steps, tr_schedule, rot_schedule, tor_sch
     return out
 
 
+def crop_receptor(g, cutoff):
+    """Device-side ``crop_beyond`` (utils/utils.py:388-413, called per step at utils/sampling.py:104-109): a view of the
+    batch whose receptor keeps only the residues within ``cutoff`` of some ligand atom of the same complex, contact edges
+    restricted and relabelled.  The reference deep-copies the batch, splits it into a Python list, crops each complex
+    and re-collates; here one neighbour-count kernel + index compaction does the same on the device.  The ligand store is
+    shared with ``g`` (the sampler keeps updating ``g['ligand'].pos``); like the reference's fresh Batch, the returned
+    graph carries no cached receptor embeddings."""
+    from .hetero import HeteroGraph, Store
+    lig, rec, rr = g['ligand'], g['receptor'], g['receptor', 'receptor']
+    B = g.num_graphs
+    lig_ptr = ops.segment_ptr(lig.batch, B)
+    _, _, count = ops.radius(lig.pos, rec.pos, lig_ptr, rec.batch, r=float(cutoff), max_num_neighbors=1)
+    keep = count > 0
+    out = HeteroGraph()
+    out._nodes['ligand'] = lig
+    for k, st in g._nodes.items():
+        if k not in ('ligand', 'receptor'):
+            out._nodes[k] = st
+    new = Store()
+    for k, v in rec.__dict__.items():
+        if k in ('rec_node_attr', 'ptr', 'node_t') or k.startswith('_'):
+            continue
+        if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == keep.shape[0]:
+            setattr(new, k, v[keep])
+        else:
+            setattr(new, k, v)
+    out._nodes['receptor'] = new
+    ei = rr.edge_index
+    ok = keep[ei[0]] & keep[ei[1]]
+    relabel = torch.cumsum(keep.long(), 0) - 1
+    out._edges[('receptor', 'receptor')] = Store(edge_index=relabel[ei[:, ok]])
+    for et, st in g._edges.items():
+        if et != ('receptor', 'receptor'):
+            out._edges[et] = st
+    for k, v in g._globals.items():
+        out._globals[k] = v
+    return out
+
+
 @torch.no_grad()
 def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
              no_random=False, ode=False, visualization_list=None, confidence_model=None, confidence_data_list=None,
@@ -84,8 +123,6 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     """``noise_fn(kind, shape) -> tensor`` (kind in 'tr','rot','tor') replaces the device RNG when given - used by the
     injected-noise parity tests; otherwise torch.normal is drawn on ``device`` in the reference's order."""
     assert not (return_full_trajectory or return_features or pivot), "Not implemented yet in new inference version"
-    if getattr(model_args, 'crop_beyond', None) is not None:
-        raise NotImplementedError("crop_beyond (utils/utils.py:388-413) is not built yet - SURVEY.md row a19")
     device = torch.device(device)
     if device.type != 'cuda':
         raise RuntimeError("diffdock_b200.sampling runs on a CUDA device only (no CPU fallback)")
@@ -111,9 +148,14 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             t_tr, t_rot, t_tor = tr_schedule[t_idx], rot_schedule[t_idx], tor_schedule[t_idx]
             coef = step_coefficients(t_idx, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_to_sigma,
                                      model_args, ode, temp_sampling, temp_psi, temp_sigma_data)
-            set_time(g, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b,
+            if getattr(model_args, 'crop_beyond', None) is not None:
+                tr_sigma = float(t_to_sigma(t_tr, t_rot, t_tor)[0])
+                mod = crop_receptor(g, tr_sigma * 3 + model_args.crop_beyond)
+            else:
+                mod = g
+            set_time(mod, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b,
                      bool(getattr(model_args, 'all_atoms', False)), device)
-            tr_score, rot_score, tor_score = model(g)[:3]
+            tr_score, rot_score, tor_score = model(mod)[:3]
             tr_score, rot_score, tor_score = _nan_guard(tr_score, rot_score, tor_score)
             zero = no_random or (no_final_step_noise and t_idx == inference_steps - 1)
             tr_z = rot_z = tor_z = None

@@ -149,6 +149,8 @@ def make_complex(n_res=200, n_atoms=20, seed=0, max_neighbors=24, rec_radius=15.
     rec = g['receptor']
     rec.x = torch.from_numpy(rx)
     rec.pos = torch.from_numpy(rpos)
+    # carried (and cropped) by utils/utils.py:crop_beyond; not read by the coarse-grained score model
+    rec.side_chain_vecs = torch.from_numpy(np.random.default_rng(seed + 7919).normal(size=(n_res, 4, 3)).astype(np.float32))
     g['receptor', 'receptor'].edge_index = torch.from_numpy(redge)
     return g
 

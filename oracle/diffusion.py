@@ -86,3 +86,20 @@ def modify_conformer_batch(orig_pos, data, tr_update, rot_update, torsion_update
     flex = torsion_update_batch(rigid, edge_index.T[edge_mask], mask_rotate, torsion_updates.reshape(B, -1))
     R, t = kabsch_batch(flex, rigid)
     return (torch.bmm(flex, R.transpose(1, 2)) + t.transpose(1, 2)).reshape(-1, 3)
+
+
+def crop_beyond(g, cutoff):
+    """utils/utils.py:388-413 (all_atoms=False): drop the residues farther than ``cutoff`` from every ligand atom, with
+    torch_geometric.utils.subgraph(..., relabel_nodes=True) restated for the receptor contact edges."""
+    lig, rec = g['ligand'].pos, g['receptor'].pos
+    keep = torch.any(torch.sum((lig.unsqueeze(0) - rec.unsqueeze(1)) ** 2, -1) < cutoff ** 2, dim=1)
+    st = g['receptor']
+    st.pos, st.x = st.pos[keep], st.x[keep]
+    if 'side_chain_vecs' in st:
+        st.side_chain_vecs = st.side_chain_vecs[keep]
+    rr = g['receptor', 'receptor']
+    ei = rr.edge_index
+    relabel = torch.cumsum(keep.long(), 0) - 1
+    ok = keep[ei[0]] & keep[ei[1]]
+    rr.edge_index = relabel[ei[:, ok]]
+    return g

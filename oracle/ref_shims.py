@@ -127,7 +127,16 @@ def install():
                 Dataset=type('Dataset', (), {}))
     loader = _mod('torch_geometric.loader', DataLoader=DataLoader, DataListLoader=DataLoader)
     _mod('torch_geometric.loader.dataloader', Collater=_Anything('Collater'))
-    utils = _mod('torch_geometric.utils', to_networkx=_Anything('to_networkx'), subgraph=_Anything('subgraph'),
+    def subgraph(subset, edge_index, edge_attr=None, relabel_nodes=False, num_nodes=None):
+        """torch_geometric.utils.subgraph for a boolean node mask: edges with both end points kept, optionally relabelled."""
+        assert subset.dtype == torch.bool
+        ok = subset[edge_index[0]] & subset[edge_index[1]]
+        ei = edge_index[:, ok]
+        if relabel_nodes:
+            ei = (torch.cumsum(subset.long(), 0) - 1)[ei]
+        return ei, (edge_attr[ok] if edge_attr is not None else None)
+
+    utils = _mod('torch_geometric.utils', to_networkx=_Anything('to_networkx'), subgraph=subgraph,
                  degree=_Anything('degree'))
     dp = _mod('torch_geometric.nn.data_parallel', DataParallel=_Anything('DataParallel'))
     tnn = _mod('torch_geometric.nn', data_parallel=dp, DataParallel=_Anything('DataParallel'))

@@ -1,11 +1,13 @@
 """Oracle restatement of the reverse-diffusion loop utils/sampling.py:69-201 (no confidence model, no
-visualisation, crop_beyond unsupported).  TEST INFRASTRUCTURE."""
+visualisation).  TEST INFRASTRUCTURE."""
 import numpy as np
 import torch
 
 from diffdock_b200.hetero import collate
 
-from .diffusion import modify_conformer_batch, set_time
+import copy
+
+from .diffusion import crop_beyond, modify_conformer_batch, set_time
 
 
 def _triple(v):
@@ -47,8 +49,13 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 dt_rot = rot_schedule[t_idx] - rot_schedule[t_idx + 1] if not last else rot_schedule[t_idx]
                 dt_tor = tor_schedule[t_idx] - tor_schedule[t_idx + 1] if not last else tor_schedule[t_idx]
                 tr_sigma, rot_sigma, tor_sigma = t_to_sigma(t_tr, t_rot, t_tor)
-                set_time(g, t_tr, t_rot, t_tor, b, device)
-                tr_score, rot_score, tor_score = model(g)[:3]
+                if getattr(a, 'crop_beyond', None) is not None:         # sampling.py:104-109
+                    mod = collate([crop_beyond(x, tr_sigma * 3 + a.crop_beyond)
+                                   for x in copy.deepcopy(g).to_data_list()])
+                else:
+                    mod = g
+                set_time(mod, t_tr, t_rot, t_tor, b, device)
+                tr_score, rot_score, tor_score = model(mod)[:3]
                 if torch.isnan(tr_score.mean(-1)).sum() > 0:            # sampling.py:117-131
                     for s in (tr_score, rot_score, tor_score):
                         eps = 0.01 * torch.nanmean(s.abs())

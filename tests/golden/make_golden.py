@@ -191,4 +191,30 @@ out_list, _ = r_sampling.sampling(data_list=data_list, model=m2, inference_steps
                                   temp_sigma_data=[0.9299802531572672, 0.7464326999906034, 0.6943254174849822])
 save('ref_sampling.pt', dict(model_case=0, steps=steps, seed=123, schedule=sched,
                              final_pos=[d['ligand'].pos.clone() for d in out_list]))
+
+# same run with per-step receptor cropping (utils/sampling.py:104-109 -> utils/utils.py:388-413)
+import utils.utils as r_utils                # noqa: E402
+kept = []
+_orig_crop = r_utils.crop_beyond
+
+
+def _spy(graph, cutoff, all_atoms):
+    _orig_crop(graph, cutoff, all_atoms)
+    kept.append(int(graph['receptor'].pos.shape[0]))
+
+
+r_sampling.crop_beyond = _spy
+data_list = copy.deepcopy(p2)
+torch.manual_seed(321)
+margs.crop_beyond = 7.0
+sched_full = sched
+sched = np.array([0.30, 0.22, 0.15, 0.08])     # late, small-sigma steps: the cut-off 3*sigma_tr + 7 A crops partially
+out_list, _ = r_sampling.sampling(data_list=data_list, model=m2, inference_steps=steps, tr_schedule=sched,
+                                  rot_schedule=sched, tor_schedule=sched, device=torch.device('cpu'),
+                                  t_to_sigma=partial(r_du.t_to_sigma, args=a2), model_args=margs, batch_size=3,
+                                  no_final_step_noise=True, temp_sampling=[1.17, 2.06, 7.04],
+                                  temp_psi=[0.73, 0.90, 0.59], temp_sigma_data=[0.93, 0.75, 0.69])
+print('residues kept per (step, pose):', kept)
+save('ref_sampling_crop.pt', dict(model_case=0, steps=steps, seed=321, schedule=sched, crop_beyond=7.0, kept=kept,
+                                  final_pos=[d['ligand'].pos.clone() for d in out_list]))
 print('done')

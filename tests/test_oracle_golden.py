@@ -113,3 +113,30 @@ def test_sampling_trajectory_matches_reference():
                       temp_sigma_data=[0.9299802531572672, 0.7464326999906034, 0.6943254174849822])
     for d, ref in zip(out, s['final_pos']):
         assert rel_err(d['ligand'].pos, ref) < 1e-4
+
+
+def test_sampling_with_crop_beyond_matches_reference():
+    """utils/sampling.py:104-109 + utils/utils.py:388-413: per-step receptor cropping (7..17 of 24 residues survive)."""
+    from oracle.diffusion import t_to_sigma
+    from oracle.sampling import sampling
+    s = load_golden('ref_sampling_crop.pt')
+    case = load_golden('ref_cg_model.pt')[s['model_case']]
+    m, poses, a = golden_model(case, 'oracle')
+    a.crop_beyond = s['crop_beyond']
+    assert 0 < min(s['kept']) and max(s['kept']) < 24
+    torch.manual_seed(s['seed'])
+    out, _ = sampling(copy.deepcopy(poses), m, s['steps'], s['schedule'], s['schedule'], s['schedule'], 'cpu',
+                      partial(t_to_sigma, args=a), a, batch_size=3, no_final_step_noise=True,
+                      temp_sampling=[1.17, 2.06, 7.04], temp_psi=[0.73, 0.90, 0.59], temp_sigma_data=[0.93, 0.75, 0.69])
+    for d, ref in zip(out, s['final_pos']):
+        assert rel_err(d['ligand'].pos, ref) < 1e-4
+
+
+def test_to_data_list_inverts_collate():
+    case = load_golden('ref_cg_model.pt')[0]
+    poses = [graph_from_dict(d) for d in case['poses']]
+    back = collate(poses).to_data_list()
+    for p, q in zip(poses, back):
+        assert torch.equal(p['ligand'].pos, q['ligand'].pos) and torch.equal(p['ligand'].edge_mask, q['ligand'].edge_mask)
+        assert torch.equal(p['receptor', 'receptor'].edge_index, q['receptor', 'receptor'].edge_index)
+        assert torch.equal(p['ligand', 'ligand'].edge_index, q['ligand', 'ligand'].edge_index)

@@ -82,3 +82,21 @@ def test_20_step_trajectory_vs_oracle_injected_noise(built_lib):
                       noise_fn=lambda k, s: torch.randn(s, generator=g2), **kw)
     worst = max(rel_err(d['ligand'].pos, r['ligand'].pos) for d, r in zip(got, ref))
     assert worst < 1e-3, worst     # 20 compounded steps through neighbour-list changes; per-step scores hold 1e-4
+
+
+def test_sampling_with_crop_beyond_matches_reference_fixture(built_lib):
+    """Device-side crop_receptor() vs the reference's deepcopy/to_data_list/crop/re-collate path (fixture)."""
+    from diffdock_b200.diffusion_utils import t_to_sigma
+    from diffdock_b200.sampling import sampling
+    s = load_golden('ref_sampling_crop.pt')
+    case = load_golden('ref_cg_model.pt')[s['model_case']]
+    m, poses, a = golden_model(case, 'product')
+    a.crop_beyond = s['crop_beyond']
+    torch.manual_seed(s['seed'])
+    noise = lambda kind, shape: torch.normal(mean=0, std=1, size=shape)
+    out, _ = sampling(copy.deepcopy(poses), m, s['steps'], s['schedule'], s['schedule'], s['schedule'], 'cuda:0',
+                      partial(t_to_sigma, args=a), a, batch_size=3, no_final_step_noise=True,
+                      temp_sampling=[1.17, 2.06, 7.04], temp_psi=[0.73, 0.90, 0.59], temp_sigma_data=[0.93, 0.75, 0.69],
+                      noise_fn=noise)
+    for d, ref in zip(out, s['final_pos']):
+        assert rel_err(d['ligand'].pos, ref) < 1e-4
