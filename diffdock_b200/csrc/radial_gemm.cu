@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/diffdock_b200.h"
 
@@ -58,6 +59,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// multicast variant: one L2 read lands in the same shared-memory offset of every CTA of the cluster in cta_mask, and
+// performs complete_tx on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -102,16 +124,20 @@ struct GemmParams {
   long long ldo;
   long long n_edges;
   int K, n_kb, n_tiles_n;
+  int debug_nostore;   // profiling aid (DDB200_GEMM_NOSTORE=1): run everything but the global stores
 };
 
+template <int CL>   // thread-block cluster size: the B' stream is multicast to the CL CTAs of a cluster
 __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (1 KB of slack is allocated)
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // layout: [A: n_kb x 16 KB][B ring: 3 x 32 KB][barriers]
+  // (offset arithmetic on the __shared__ symbol keeps the pointers in the shared address space: LDS/STS, not generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // layout: [A: n_kb x 16 KB][B ring: 3 x 32 KB][epilogue transpose buffers][barriers]
   unsigned char* sA = smem;
   unsigned char* sB = smem + (size_t)p.n_kb * A_KB_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  unsigned char* sStage = sB + STAGES * B_STAGE_BYTES;            // 4 epilogue warps x 32 x 33 floats (transpose buffer)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 4 * 32 * 33 * 4);
   uint64_t* full = bars;               // [STAGES]
   uint64_t* empty = bars + STAGES;     // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES; // [2]
@@ -120,7 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -131,8 +157,11 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();     // every CTA's barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -143,7 +172,10 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
   uint32_t ma = 0;   // MMA accumulator counter    (buf = ma & 1, phase = (ma >> 1) & 1)
   uint32_t ea = 0;   // epilogue accumulator counter
 
-  for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+  // a cluster walks CL consecutive edge tiles at a time in lock step (coupled through the shared B' stream); a CTA whose
+  // tile index falls past the end still drains the pipeline on an all-zero tile
+  for (long long mt0 = (long long)(blockIdx.x / CL) * CL; mt0 < n_mtiles; mt0 += gridDim.x) {
+    const long long mt = mt0 + crank;
     __syncthreads();   // previous tile fully drained (epilogue passed its last tmem_full => all MMAs that read A are done)
     // ---- build the A' image: rows = edges, cols = [hi | hi | lo] of H, 128B-swizzled, zero padded ----------------
     {
@@ -181,11 +213,15 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
         for (int nt = 0; nt < p.n_tiles_n; ++nt)
           for (int kb = 0; kb < p.n_kb; ++kb, ++pc) {
             const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
+            mbar_wait(&empty[s], ph ^ 1);       // all CL CTAs have consumed this stage
             mbar_expect_tx(&full[s], B_STAGE_BYTES);
-            bulk_g2s(sB + (size_t)s * B_STAGE_BYTES,
-                     reinterpret_cast<const unsigned char*>(p.bimg) + ((size_t)nt * p.n_kb + kb) * B_STAGE_BYTES,
-                     B_STAGE_BYTES, &full[s]);
+            const unsigned char* src =
+                reinterpret_cast<const unsigned char*>(p.bimg) + ((size_t)nt * p.n_kb + kb) * B_STAGE_BYTES;
+            if constexpr (CL == 1) {
+              bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s]);
+            } else if (crank == 0) {
+              bulk_g2s_mcast(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s], kMask);
+            }
           }
       }
     } else if (warp == 1) {
@@ -204,35 +240,47 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk)
               umma_bf16(d, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kb | kk) != 0);
-            umma_commit(&empty[s]);     // stage free once these MMAs have read it
+            if constexpr (CL == 1) umma_commit(&empty[s]);     // stage free once these MMAs have read it
+            else umma_commit_mcast(&empty[s], kMask);          // ... signalled to every CTA of the cluster
           }
           umma_commit(&tfull[buf]);     // accumulator complete
         }
       }
     } else if (warp >= 4) {
-      // ===== epilogue: TMEM -> registers -> + bias -> global ===================================================
+      // ===== epilogue: TMEM -> registers -> smem transpose -> + bias -> coalesced global stores ====================
+      // (a thread owns one accumulator row; storing rows directly would scatter 16-byte pieces over 32 rows per
+      //  instruction, so each 32x32 block is transposed through a padded shared buffer and written as 128-byte rows)
       const int q = warp & 3;                     // TMEM lane quadrant this warp may access
-      const long long e = mt * BM + q * 32 + lane;
+      float* stg = reinterpret_cast<float*>(sStage) + (size_t)q * 32 * 33;
+      const long long e_base = mt * BM + q * 32;
       for (int nt = 0; nt < p.n_tiles_n; ++nt, ++ea) {
         const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
         mbar_wait(&tfull[buf], aph);
         tc_fence_after();
-        float* orow = p.out + e * p.ldo + (long long)nt * BN;
-        const float* brow = p.bias + (long long)nt * BN;
+        const int nrow = (int)((p.n_edges - e_base) < 32 ? (p.n_edges - e_base) : 32);
+        float* obase = p.out + e_base * p.ldo + (long long)nt * BN + lane;
+        const float* bbase = p.bias + (long long)nt * BN + lane;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
-          if (e < p.n_edges) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c * 32 + j));
-              float4 o;
-              o.x = __uint_as_float(v[j]) + b.x; o.y = __uint_as_float(v[j + 1]) + b.y;
-              o.z = __uint_as_float(v[j + 2]) + b.z; o.w = __uint_as_float(v[j + 3]) + b.w;
-              *reinterpret_cast<float4*>(orow + c * 32 + j) = o;
-            }
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          const float b = __ldg(bbase + c * 32);
+          float* o = obase + c * 32;
+          if (p.debug_nostore) {
+            float acc = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) acc += stg[rr * 33 + lane] + b;
+            if (acc == 1.2345e-30f) o[0] = acc;
+          } else if (nrow == 32) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) o[(long long)rr * p.ldo] = stg[rr * 33 + lane] + b;
+          } else {
+            for (int rr = 0; rr < nrow; ++rr) o[(long long)rr * p.ldo] = stg[rr * 33 + lane] + b;
           }
+          __syncwarp();
         }
         tc_fence_before();
         __syncwarp();
@@ -242,6 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();     // nobody leaves while a peer may still signal its barriers
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -261,18 +310,40 @@ extern "C" int ddb200_radial_gemm(const float* h, int64_t ldh, int64_t n_edges, 
   GemmParams p;
   p.h = h; p.ldh = ldh; p.bimg = reinterpret_cast<const __nv_bfloat16*>(b_images); p.bias = bias; p.out = out;
   p.ldo = ldo; p.n_edges = n_edges; p.K = K; p.n_kb = n_kb; p.n_tiles_n = n_tiles_n;
-  const size_t smem = (size_t)n_kb * A_KB_BYTES + STAGES * B_STAGE_BYTES + 16 * sizeof(uint64_t) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(radial_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+  { const char* ns = getenv("DDB200_GEMM_NOSTORE"); p.debug_nostore = (ns && ns[0] == '1') ? 1 : 0; }
+  const size_t smem = (size_t)n_kb * A_KB_BYTES + STAGES * B_STAGE_BYTES + 4 * 32 * 33 * 4 + 16 * sizeof(uint64_t) + 1024;
+  static int cluster = -1;
+  if (cluster < 0) {
+    const char* e = getenv("DDB200_GEMM_CLUSTER");
+    cluster = e ? atoi(e) : 1;
+    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
+    cudaError_t err = cudaFuncSetAttribute(radial_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(radial_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(radial_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err != cudaSuccess) { cluster = -1; return (int)err; }
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_mtiles = (n_edges + BM - 1) / BM;
-  const unsigned grid = (unsigned)(n_mtiles < sms ? n_mtiles : sms);
-  radial_gemm_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+  const int cl = (n_mtiles >= 2 * cluster) ? cluster : 1;
+  long long grid = (n_mtiles + cl - 1) / cl * cl;
+  const long long cap = (long long)(sms / cl) * cl;
+  if (grid > cap) grid = cap;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le;
+  if (cl == 1) le = cudaLaunchKernelEx(&cfg, radial_gemm_kernel<1>, p);
+  else if (cl == 2) le = cudaLaunchKernelEx(&cfg, radial_gemm_kernel<2>, p);
+  else le = cudaLaunchKernelEx(&cfg, radial_gemm_kernel<4>, p);
+  if (le != cudaSuccess) return (int)le;
   return (int)cudaGetLastError();
 }

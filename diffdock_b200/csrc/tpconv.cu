@@ -27,6 +27,8 @@ constexpr int HDR = 32;
 constexpr int ERUN = 32;          // edges per work unit (one lane holds one edge's indices/geometry)
 constexpr int MAX_XREG = 8;       // register prefetch of the next source row covers D_in <= 256
 constexpr uint32_t MAGIC = 0x44423232u;
+template <int N>
+struct IC { static constexpr int value = N; };
 
 struct KParams {
   const float* x; long long x_stride;
@@ -68,6 +70,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {   // exactly one lane of the (converged) warp gets true
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
@@ -179,28 +186,42 @@ __global__ void __launch_bounds__(512, 1) tpconv_accumulate_kernel(const KParams
   const long long gw = (long long)blockIdx.x * p.warps + warp;
   const uint64_t policy = policy_evict_first();
 
-  // ---- producer cursor (all lanes track it, lane 0 issues) -----------------------------------------------------
-  long long p_unit = gw, p_e = gw * ERUN;
-  int p_c = 0, p_stage = 0;
+  // ---- producer cursor: warp-uniform state, one elected lane issues ------------------------------------------
+  // Kept cheap on purpose: it runs once per TMA chunk (~16 times per edge).  Row pointer and edge countdown are
+  // advanced incrementally; stage / barrier operands are 32-bit shared-window addresses.
+  const uint32_t stage_u32 = smem_u32(stage_base), bar_u32 = smem_u32(mybar);
+  const uint32_t stage_bytes = (uint32_t)p.stage_floats * 4u;
+  const long long row_bytes = p.w_stride * 4;
+  const char* const w_bytes = reinterpret_cast<const char*>(p.w);
+  long long p_unit = gw;
+  bool p_valid = gw < n_units;
+  const char* p_row = w_bytes + gw * ERUN * row_bytes;
+  int p_left = p_valid ? (int)((E - gw * ERUN) < ERUN ? (E - gw * ERUN) : ERUN) : 0;
+  int p_c = 0;
+  uint32_t p_stage = 0;
   auto issue_next = [&]() {
-    if (p_unit < n_units) {
-      if (lane == 0) {
-        const int* ch = chunks + 4 * p_c;
-        const uint32_t bytes = (uint32_t)ch[3] * 4u;
-        mbar_expect_tx(&mybar[p_stage], bytes);
-        bulk_g2s(stage_base + (size_t)p_stage * p.stage_floats, p.w + p_e * p.w_stride + ch[2], bytes,
-                 &mybar[p_stage], policy);
+    if (p_valid) {
+      const int goff = chunks[4 * p_c + 2], nfl = chunks[4 * p_c + 3];
+      if (elect_one()) {
+        const uint32_t bar = bar_u32 + p_stage * 8u, bytes = (uint32_t)nfl * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+            ::"r"(stage_u32 + p_stage * stage_bytes), "l"(p_row + (long long)goff * 4), "r"(bytes), "r"(bar), "l"(policy)
+            : "memory");
       }
       if (++p_c == n_chunks) {
         p_c = 0;
-        long long uend = (p_unit + 1) * ERUN;
-        if (uend > E) uend = E;
-        if (++p_e >= uend) {
+        p_row += row_bytes;
+        if (--p_left == 0) {
           p_unit += TW;
-          p_e = p_unit * ERUN;
+          p_valid = p_unit < n_units;
+          p_row = w_bytes + p_unit * ERUN * row_bytes;
+          const long long rem = E - p_unit * ERUN;
+          p_left = (int)(rem < ERUN ? rem : ERUN);
         }
       }
-      p_stage = (p_stage + 1 == p.stages) ? 0 : p_stage + 1;
+      p_stage = (p_stage + 1 == (uint32_t)p.stages) ? 0u : p_stage + 1;
     }
   };
   for (int s = 0; s < p.stages; ++s) issue_next();
@@ -356,39 +377,21 @@ __global__ void __launch_bounds__(512, 1) tpconv_accumulate_kernel(const KParams
         const int4* tiles4 = reinterpret_cast<const int4*>(tiles);
         const float* st = stage_base;
         int t = 0;
-        while (t < n_tiles) {
-          const int4 gb = tiles4[4 * t + 1], gc = tiles4[4 * t + 2];
-          const int rs = gb.x, dout = gb.y, vec = gb.z, li = gb.w, R = gc.x, accb = gc.y, zstr = gc.z, kind = gc.w;
-          const int r = li == 0 ? lr[0] : (li == 1 ? lr[1] : (li == 2 ? lr[2] : lr[3]));
-          const int cc = li == 0 ? lc[0] : (li == 1 ? lc[1] : (li == 2 ? lc[2] : lc[3]));
-          const bool active = r < R;
-          const int woff = r * rs + cc * vec, zoff = r * zstr, wstep = R * rs, zstep = R * zstr;
-          float acc[12];
+        // tile loop of one accumulator run, specialised on (vector width, 2l+1); also drives the TMA ring
+        auto run_group = [&](auto vec_c, auto dout_c, int woff, int zoff, int wstep, int zstep, bool active, int r,
+                             float* as) {
+          constexpr int VEC = decltype(vec_c)::value, DOUT = decltype(dout_c)::value;
+          float acc[VEC * DOUT];
 #pragma unroll
-          for (int q = 0; q < 12; ++q) acc[q] = 0.f;
+          for (int q = 0; q < VEC * DOUT; ++q) acc[q] = 0.f;
           for (;;) {
             const int4 ta = tiles4[4 * t];
             if (ta.w & 4) {      // first tile of a TMA chunk: wait for its stage
               while (!mbar_try_wait(&mybar[c_stage], c_par)) {}
-              st = stage_base + (size_t)c_stage * p.stage_floats;
+              st = stage_base + c_stage * p.stage_floats;
             }
             const int n_it = active ? (ta.z & 0xffff) + (r < (ta.z >> 16) ? 1 : 0) : 0;
-            const float* wp = st + ta.x + woff;
-            const float* zp = zs + ta.y + zoff;
-            switch (kind) {
-              case 1: run_rows<4, 1>(wp, zp, n_it, wstep, zstep, acc); break;
-              case 2: run_rows<4, 3>(wp, zp, n_it, wstep, zstep, acc); break;
-              case 3: run_rows<2, 1>(wp, zp, n_it, wstep, zstep, acc); break;
-              case 4: run_rows<2, 3>(wp, zp, n_it, wstep, zstep, acc); break;
-              default: {   // keep acc[] in registers: the out-of-line generic path works on a private copy
-                float tmp[9];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) tmp[q] = acc[q];
-                run_rows_generic(wp, zp, n_it, wstep, zstep, dout, tmp);
-#pragma unroll
-                for (int q = 0; q < 9; ++q) acc[q] = tmp[q];
-              } break;
-            }
+            run_rows<VEC, DOUT>(st + ta.x + woff, zs + ta.y + zoff, n_it, wstep, zstep, acc);
             if (ta.w & 8) {      // last tile of the chunk: hand the stage back to the TMA producer
               __syncwarp();
               issue_next();
@@ -397,11 +400,45 @@ __global__ void __launch_bounds__(512, 1) tpconv_accumulate_kernel(const KParams
             ++t;
             if (ta.w & 2) break;
           }
-          float* as = racc + accb + lane;
-          const int nq = vec * dout;
 #pragma unroll
-          for (int q = 0; q < 12; ++q)
-            if (q < nq) as[q * WARP] += acc[q];
+          for (int q = 0; q < VEC * DOUT; ++q) as[q * WARP] += acc[q];
+        };
+        while (t < n_tiles) {
+          const int4 gb = tiles4[4 * t + 1], gc = tiles4[4 * t + 2];
+          const int rs = gb.x, dout = gb.y, vec = gb.z, li = gb.w, R = gc.x, accb = gc.y, zstr = gc.z, kind = gc.w;
+          const int r = li == 0 ? lr[0] : (li == 1 ? lr[1] : (li == 2 ? lr[2] : lr[3]));
+          const int cc = li == 0 ? lc[0] : (li == 1 ? lc[1] : (li == 2 ? lc[2] : lc[3]));
+          const bool active = r < R;
+          const int woff = r * rs + cc * vec, zoff = r * zstr, wstep = R * rs, zstep = R * zstr;
+          float* as = racc + accb + lane;
+          switch (kind) {
+            case 1: run_group(IC<4>{}, IC<1>{}, woff, zoff, wstep, zstep, active, r, as); break;
+            case 2: run_group(IC<4>{}, IC<3>{}, woff, zoff, wstep, zstep, active, r, as); break;
+            case 3: run_group(IC<2>{}, IC<1>{}, woff, zoff, wstep, zstep, active, r, as); break;
+            case 4: run_group(IC<2>{}, IC<3>{}, woff, zoff, wstep, zstep, active, r, as); break;
+            default: {   // generic: scalar weight loads, any 2l+1 <= 9, accumulators in a private (stack) array
+              float acc[9];
+#pragma unroll
+              for (int q = 0; q < 9; ++q) acc[q] = 0.f;
+              for (;;) {
+                const int4 ta = tiles4[4 * t];
+                if (ta.w & 4) {
+                  while (!mbar_try_wait(&mybar[c_stage], c_par)) {}
+                  st = stage_base + c_stage * p.stage_floats;
+                }
+                const int n_it = active ? (ta.z & 0xffff) + (r < (ta.z >> 16) ? 1 : 0) : 0;
+                run_rows_generic(st + ta.x + woff, zs + ta.y + zoff, n_it, wstep, zstep, dout, acc);
+                if (ta.w & 8) {
+                  __syncwarp();
+                  issue_next();
+                  if (++c_stage == p.stages) { c_stage = 0; c_par ^= 1u; }
+                }
+                ++t;
+                if (ta.w & 2) break;
+              }
+              for (int q = 0; q < vec * dout; ++q) as[q * WARP] += acc[q];
+            } break;
+          }
         }
       }
     }

@@ -18,7 +18,7 @@ from .tp_table import build_table
 ACTIVATIONS = {'relu': nn.ReLU, 'silu': nn.SiLU}
 
 # upper bound on the bytes of per-edge tensor-product weights materialised at once (edges are processed in blocks)
-WEIGHT_BLOCK_BYTES = 6 << 30
+WEIGHT_BLOCK_BYTES = 16 << 30
 
 
 def get_irrep_seq(ns, nv, use_second_order_repr, reduce_pseudoscalars):

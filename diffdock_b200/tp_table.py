@@ -20,6 +20,7 @@ M[i, k] = coef * edge_weight * sum_j C[i, j, k] * Y[j].
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import List
 
@@ -144,7 +145,9 @@ def _faster_paths(ins, shs, outs):
     return paths, off
 
 
-def build_table(in_irreps, sh_irreps, out_irreps, kind='fctp', sh_from_vector=True, stage_floats=512) -> TpTable:
+def build_table(in_irreps, sh_irreps, out_irreps, kind='fctp', sh_from_vector=True, stage_floats=None) -> TpTable:
+    if stage_floats is None:   # TMA chunk size: 3 KB measured best on B200 (16 warps x 2 stages), see profiles/
+        stage_floats = int(os.environ.get('DDB200_TPCONV_STAGE_FLOATS', 768))
     ins, shs, outs = parse_irreps(in_irreps), parse_irreps(sh_irreps), parse_irreps(out_irreps)
     if kind == 'fctp':
         paths, numel = _fctp_paths(ins, shs, outs)
