@@ -25,6 +25,8 @@ SIGNATURES = {
     'ddb200_pose_update': (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp,
                                   _vp]),
     'ddb200_radial_gemm': (_int, [_vp, _i64, _i64, _int, _vp, _vp, _int, _vp, _i64, _vp]),
+    'ddb200_radial_mlp': (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _i64, _vp,
+                                 _i64, _vp]),
 }
 
 

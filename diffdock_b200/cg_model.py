@@ -311,10 +311,11 @@ class CGModel(nn.Module):
             vec = torch.cat([g[3] for g in use])
             ew = torch.cat([g[4] if torch.is_tensor(g[4]) else torch.ones((g[0].shape[0], 1), device=node.device)
                             for g in use]) if smooth else 1.0
-            ea = [torch.cat([g[2], node[g[0], :ns], node[g[1], :ns]], -1) for g in use]
+            ea = [g[2] for g in use]          # end-point scalars are gathered inside the radial-MLP kernel
             if not self.differentiate_convolutions:
                 ea = torch.cat(ea, 0)
-            node = layer(node, torch.stack([tgt, src]), ea, None, edge_weight=ew, edge_vec=vec, assume_sorted=True)
+            node = layer(node, torch.stack([tgt, src]), ea, None, edge_weight=ew, edge_vec=vec, assume_sorted=True,
+                         gather_scalars=ns)
         lig_node = node[:n_lig]
 
         # -- translation / rotation head (:368-395) -----------------------------------------------------------------

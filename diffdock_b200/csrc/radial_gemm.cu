@@ -115,6 +115,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// element (row r, column col) of a K-major, 128B-swizzled operand image made of 16 KB k-blocks of 64 columns
+__device__ __forceinline__ void put_a(unsigned char* sA, int r, int col, __nv_bfloat16 v) {
+  const int kb = col >> 6, c = (col & 63) >> 3, j = col & 7;
+  *reinterpret_cast<__nv_bfloat16*>(sA + (size_t)kb * A_KB_BYTES + r * 128 + ((c ^ (r & 7)) << 4) + j * 2) = v;
+}
+
 struct GemmParams {
   const float* h;        // [E, K] fp32, row stride ldh
   long long ldh;
@@ -124,6 +130,13 @@ struct GemmParams {
   long long ldo;
   long long n_edges;
   int K, n_kb, n_tiles_n;
+  // optional in-kernel first layer (h == nullptr): H = relu([ea | node[tgt,:ns] | node[src,:ns]] @ W1^T + b1)
+  const float* ea; long long ld_ea; int ne;
+  const float* node; long long ld_node; int ns;
+  const int* tgt; const int* src;
+  const __nv_bfloat16* w1img;   // [n_kb1][256 rows][64] swizzled images of W1 ([H | pad] x K1)
+  const float* b1;
+  int K1, n_kb1;
   int debug_nostore;   // profiling aid (DDB200_GEMM_NOSTORE=1): run everything but the global stores
 };
 
@@ -142,12 +155,14 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
   uint64_t* empty = bars + STAGES;     // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES; // [2]
   uint64_t* tempty = tfull + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* a_ready = tempty + 2;      // [1] hidden activations written back as the A' image (fused first layer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    mbar_init(a_ready, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // TMEM: all 512 columns (two 256-column fp32 accumulators)
@@ -166,6 +181,10 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
   // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+  const bool fuse1 = (p.h == nullptr);
+  const int n1 = ((p.K + 15) / 16) * 16;     // first-layer MMA N (hidden width rounded to the UMMA granularity)
+  const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n1 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  uint32_t mtc = 0;  // edge tiles processed by this CTA (phase of a_ready)
   const long long n_mtiles = (p.n_edges + BM - 1) / BM;
   uint32_t pc = 0;   // producer k-block counter   (stage = pc % STAGES, phase = (pc / STAGES) & 1)
   uint32_t mc = 0;   // MMA k-block counter
@@ -177,31 +196,35 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
   for (long long mt0 = (long long)(blockIdx.x / CL) * CL; mt0 < n_mtiles; mt0 += gridDim.x) {
     const long long mt = mt0 + crank;
     __syncthreads();   // previous tile fully drained (epilogue passed its last tmem_full => all MMAs that read A are done)
-    // ---- build the A' image: rows = edges, cols = [hi | hi | lo] of H, 128B-swizzled, zero padded ----------------
+    // ---- build the first MMA operand image: rows = edges, cols = [hi | hi | lo], 128B-swizzled, zero padded ----------
     {
       const long long e0 = mt * BM;
-      const int K = p.K;
-      const int kpad = p.n_kb * BK;
-      // zero the padding columns [3K, kpad)
-      for (int idx = tid; idx < BM * (kpad - 3 * K); idx += THREADS) {
-        const int r = idx / (kpad - 3 * K), col = 3 * K + idx % (kpad - 3 * K);
-        const int kb = col >> 6, c = (col & 63) >> 3, j = col & 7;
-        *reinterpret_cast<__nv_bfloat16*>(sA + (size_t)kb * A_KB_BYTES + r * 128 + ((c ^ (r & 7)) << 4) + j * 2) =
-            __float2bfloat16(0.f);
+      const int Kin = fuse1 ? p.K1 : p.K;                     // width of what is split here
+      const int kpad = (fuse1 ? p.n_kb1 : p.n_kb) * BK;
+      for (int idx = tid; idx < BM * (kpad - 3 * Kin); idx += THREADS) {   // padding columns [3K, kpad)
+        const int r = idx / (kpad - 3 * Kin), col = 3 * Kin + idx % (kpad - 3 * Kin);
+        put_a(sA, r, col, __float2bfloat16(0.f));
       }
-      for (int idx = tid; idx < BM * K; idx += THREADS) {
-        const int r = idx / K, k = idx - r * K;
+      for (int idx = tid; idx < BM * Kin; idx += THREADS) {
+        const int r = idx / Kin, k = idx - r * Kin;
         const long long e = e0 + r;
-        const float v = (e < p.n_edges) ? __ldg(p.h + e * p.ldh + k) : 0.f;
+        float v = 0.f;
+        if (e < p.n_edges) {
+          if (!fuse1) {
+            v = __ldg(p.h + e * p.ldh + k);
+          } else if (k < p.ne) {                                 // per-edge attribute
+            v = __ldg(p.ea + e * p.ld_ea + k);
+          } else if (k < p.ne + p.ns) {                          // scalars of the target node (models/cg_model.py:343)
+            v = __ldg(p.node + (long long)__ldg(p.tgt + e) * p.ld_node + (k - p.ne));
+          } else {                                               // scalars of the gathered (source) node
+            v = __ldg(p.node + (long long)__ldg(p.src + e) * p.ld_node + (k - p.ne - p.ns));
+          }
+        }
         const __nv_bfloat16 hi = __float2bfloat16(v);
         const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-#pragma unroll
-        for (int part = 0; part < 3; ++part) {
-          const int col = part * K + k;
-          const int kb = col >> 6, c = (col & 63) >> 3, j = col & 7;
-          *reinterpret_cast<__nv_bfloat16*>(sA + (size_t)kb * A_KB_BYTES + r * 128 + ((c ^ (r & 7)) << 4) + j * 2) =
-              (part == 2) ? lo : hi;
-        }
+        put_a(sA, r, k, hi);
+        put_a(sA, r, Kin + k, hi);
+        put_a(sA, r, 2 * Kin + k, lo);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
     }
@@ -210,6 +233,18 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
     if (warp == 0) {
       // ===== B producer =====================================================================================
       if (lane == 0) {
+        if (fuse1)
+          for (int kb = 0; kb < p.n_kb1; ++kb, ++pc) {
+            const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], B_STAGE_BYTES);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.w1img) + (size_t)kb * B_STAGE_BYTES;
+            if constexpr (CL == 1) {
+              bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s]);
+            } else if (crank == 0) {
+              bulk_g2s_mcast(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s], kMask);
+            }
+          }
         for (int nt = 0; nt < p.n_tiles_n; ++nt)
           for (int kb = 0; kb < p.n_kb; ++kb, ++pc) {
             const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
@@ -227,6 +262,27 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
     } else if (warp == 1) {
       // ===== MMA issuer ======================================================================================
       if (lane == 0) {
+        if (fuse1) {   // hidden = A0' x W1'^T into an accumulator buffer, then wait for the epilogue to turn it into A'
+          const uint32_t buf = ma & 1, aph = (ma >> 1) & 1;
+          mbar_wait(&tempty[buf], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + buf * BN;
+          for (int kb = 0; kb < p.n_kb1; ++kb, ++mc) {
+            const uint32_t s = mc % STAGES, ph = (mc / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA + (size_t)kb * A_KB_BYTES), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_bf16(d, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc1, (kb | kk) != 0);
+            if constexpr (CL == 1) umma_commit(&empty[s]);
+            else umma_commit_mcast(&empty[s], kMask);
+          }
+          umma_commit(&tfull[buf]);
+          ++ma;
+          mbar_wait(a_ready, mtc & 1);
+          tc_fence_after();
+        }
         for (int nt = 0; nt < p.n_tiles_n; ++nt, ++ma) {
           const uint32_t buf = ma & 1, aph = (ma >> 1) & 1;
           mbar_wait(&tempty[buf], aph ^ 1);
@@ -253,6 +309,34 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
       const int q = warp & 3;                     // TMEM lane quadrant this warp may access
       float* stg = reinterpret_cast<float*>(sStage) + (size_t)q * 32 * 33;
       const long long e_base = mt * BM + q * 32;
+      if (fuse1) {   // hidden activations: + bias, ReLU, bf16 split, written back over the operand image as A'
+        const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
+        mbar_wait(&tfull[buf], aph);
+        tc_fence_after();
+        const int r = q * 32 + lane, K = p.K, kpad = p.n_kb * BK;
+        for (int c0 = 0; c0 < K; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int k = c0 + j;
+            if (k < K) {
+              const float hval = fmaxf(__uint_as_float(v[j]) + __ldg(p.b1 + k), 0.f);
+              const __nv_bfloat16 hi = __float2bfloat16(hval);
+              const __nv_bfloat16 lo = __float2bfloat16(hval - __bfloat162float(hi));
+              put_a(sA, r, k, hi);
+              put_a(sA, r, K + k, hi);
+              put_a(sA, r, 2 * K + k, lo);
+            }
+          }
+        }
+        for (int col = 3 * K; col < kpad; ++col) put_a(sA, r, col, __float2bfloat16(0.f));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&tempty[buf]); mbar_arrive(a_ready); }
+        ++ea;
+      }
       for (int nt = 0; nt < p.n_tiles_n; ++nt, ++ea) {
         const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
         mbar_wait(&tfull[buf], aph);
@@ -287,6 +371,7 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
         if (lane == 0) mbar_arrive(&tempty[buf]);
       }
     }
+    ++mtc;
   }
   tc_fence_before();
   __syncthreads();
@@ -298,20 +383,10 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
 
 }  // namespace
 
-extern "C" int ddb200_radial_gemm(const float* h, int64_t ldh, int64_t n_edges, int K, const void* b_images,
-                                  const float* bias, int n_tiles_n, float* out, int64_t ldo, void* stream) {
-  if (!h || !b_images || !bias || !out || n_edges < 0 || K <= 0 || n_tiles_n <= 0) return DDB200_EINVAL;
-  const int n_kb = (3 * K + BK - 1) / BK;
-  if (n_kb > MAX_KB || ldo < (int64_t)n_tiles_n * BN || (ldo & 3) || ldh < K) return DDB200_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(b_images) & 127) ||
-      (reinterpret_cast<uintptr_t>(bias) & 15))
-    return DDB200_EINVAL;
-  if (n_edges == 0) return 0;
-  GemmParams p;
-  p.h = h; p.ldh = ldh; p.bimg = reinterpret_cast<const __nv_bfloat16*>(b_images); p.bias = bias; p.out = out;
-  p.ldo = ldo; p.n_edges = n_edges; p.K = K; p.n_kb = n_kb; p.n_tiles_n = n_tiles_n;
+static int launch_radial(GemmParams& p, void* stream) {
+  const int n_kb_max = p.n_kb > p.n_kb1 ? p.n_kb : p.n_kb1;
+  const size_t smem = (size_t)n_kb_max * A_KB_BYTES + STAGES * B_STAGE_BYTES + 4 * 32 * 33 * 4 + 16 * sizeof(uint64_t) + 1024;
   { const char* ns = getenv("DDB200_GEMM_NOSTORE"); p.debug_nostore = (ns && ns[0] == '1') ? 1 : 0; }
-  const size_t smem = (size_t)n_kb * A_KB_BYTES + STAGES * B_STAGE_BYTES + 4 * 32 * 33 * 4 + 16 * sizeof(uint64_t) + 1024;
   static int cluster = -1;
   if (cluster < 0) {
     const char* e = getenv("DDB200_GEMM_CLUSTER");
@@ -325,7 +400,7 @@ extern "C" int ddb200_radial_gemm(const float* h, int64_t ldh, int64_t n_edges, 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long n_mtiles = (n_edges + BM - 1) / BM;
+  const long long n_mtiles = (p.n_edges + BM - 1) / BM;
   const int cl = (n_mtiles >= 2 * cluster) ? cluster : 1;
   long long grid = (n_mtiles + cl - 1) / cl * cl;
   const long long cap = (long long)(sms / cl) * cl;
@@ -346,4 +421,43 @@ extern "C" int ddb200_radial_gemm(const float* h, int64_t ldh, int64_t n_edges, 
   else le = cudaLaunchKernelEx(&cfg, radial_gemm_kernel<4>, p);
   if (le != cudaSuccess) return (int)le;
   return (int)cudaGetLastError();
+}
+
+extern "C" int ddb200_radial_gemm(const float* h, int64_t ldh, int64_t n_edges, int K, const void* b_images,
+                                  const float* bias, int n_tiles_n, float* out, int64_t ldo, void* stream) {
+  if (!h || !b_images || !bias || !out || n_edges < 0 || K <= 0 || n_tiles_n <= 0) return DDB200_EINVAL;
+  const int n_kb = (3 * K + BK - 1) / BK;
+  if (n_kb > MAX_KB || ldo < (int64_t)n_tiles_n * BN || (ldo & 3) || ldh < K) return DDB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(b_images) & 127) ||
+      (reinterpret_cast<uintptr_t>(bias) & 15))
+    return DDB200_EINVAL;
+  if (n_edges == 0) return 0;
+  GemmParams p = {};
+  p.h = h; p.ldh = ldh; p.bimg = reinterpret_cast<const __nv_bfloat16*>(b_images); p.bias = bias; p.out = out;
+  p.ldo = ldo; p.n_edges = n_edges; p.K = K; p.n_kb = n_kb; p.n_tiles_n = n_tiles_n;
+  return launch_radial(p, stream);
+}
+
+extern "C" int ddb200_radial_mlp(const float* edge_attr, int64_t ld_ea, int ne, const float* node, int64_t ld_node,
+                                 int ns, const int32_t* tgt, const int32_t* src, const void* w1_images,
+                                 const float* b1, int hidden, const void* w2_images, const float* b2, int n_tiles_n,
+                                 int64_t n_edges, float* out, int64_t ldo, void* stream) {
+  if (!edge_attr || !w1_images || !b1 || !w2_images || !b2 || !out || n_edges < 0 || ne <= 0 || ns < 0 || hidden <= 0 ||
+      n_tiles_n <= 0)
+    return DDB200_EINVAL;
+  if (ns > 0 && (!node || !tgt || !src || ld_node < ns)) return DDB200_EINVAL;
+  const int K1 = ne + 2 * ns;
+  const int n_kb = (3 * hidden + BK - 1) / BK, n_kb1 = (3 * K1 + BK - 1) / BK;
+  if (n_kb > MAX_KB || n_kb1 > MAX_KB || hidden > BN || ldo < (int64_t)n_tiles_n * BN || (ldo & 3) || ld_ea < ne)
+    return DDB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(w1_images) & 127) ||
+      (reinterpret_cast<uintptr_t>(w2_images) & 127) || (reinterpret_cast<uintptr_t>(b2) & 15))
+    return DDB200_EINVAL;
+  if (n_edges == 0) return 0;
+  GemmParams p = {};
+  p.h = nullptr; p.bimg = reinterpret_cast<const __nv_bfloat16*>(w2_images); p.bias = b2; p.out = out; p.ldo = ldo;
+  p.n_edges = n_edges; p.K = hidden; p.n_kb = n_kb; p.n_tiles_n = n_tiles_n;
+  p.ea = edge_attr; p.ld_ea = ld_ea; p.ne = ne; p.node = node; p.ld_node = ld_node; p.ns = ns; p.tgt = tgt; p.src = src;
+  p.w1img = reinterpret_cast<const __nv_bfloat16*>(w1_images); p.b1 = b1; p.K1 = K1; p.n_kb1 = n_kb1;
+  return launch_radial(p, stream);
 }

@@ -59,3 +59,24 @@ def radial_gemm(h: torch.Tensor, images: torch.Tensor, bias: torch.Tensor, n_til
     _lib.check(rc, 'ddb200_radial_gemm')
     PROFILE.all_launches += 1
     return out
+
+
+def radial_mlp(edge_attr, node, ns, tgt32, src32, w1_images, b1, hidden, w2_images, b2, n_tiles, out=None):
+    """Whole two-layer radial MLP in one kernel (ddb200_radial_mlp): gathers the end-point scalars ``node[:, :ns]`` itself
+    (``ns == 0``: ``edge_attr`` already holds every input column)."""
+    _need_cuda(edge_attr, w1_images, w2_images)
+    E, ne = edge_attr.shape
+    assert edge_attr.dtype == torch.float32 and edge_attr.stride(1) == 1
+    if ns:
+        assert node.dtype == torch.float32 and node.stride(1) == 1 and node.shape[1] >= ns
+        assert tgt32.dtype == torch.int32 and src32.dtype == torch.int32 and tgt32.is_contiguous() and src32.is_contiguous()
+    ldo = n_tiles * BN
+    if out is None:
+        out = torch.empty((E, ldo), dtype=torch.float32, device=edge_attr.device)
+    rc = _lib.lib().ddb200_radial_mlp(_ptr(edge_attr), edge_attr.stride(0), ne, _ptr(node) if ns else C.c_void_p(0),
+                                      node.stride(0) if ns else 0, ns, _ptr(tgt32) if ns else C.c_void_p(0),
+                                      _ptr(src32) if ns else C.c_void_p(0), _ptr(w1_images), _ptr(b1), hidden,
+                                      _ptr(w2_images), _ptr(b2), n_tiles, E, _ptr(out), out.stride(0), _stream())
+    _lib.check(rc, 'ddb200_radial_mlp')
+    PROFILE.all_launches += 1
+    return out

@@ -135,6 +135,7 @@ class TensorProductConvLayer(nn.Module):
         self.batch_norm = IrrepsBatchNorm(out_irreps) if batch_norm else None
         self._wcache = {}
         self._gcache = {}
+        self._fcache = {}
 
     # -- radial MLP -> per-edge weights in kernel layout ------------------------------------------------------
     def _last_linear(self, fc, table):
@@ -153,6 +154,30 @@ class TensorProductConvLayer(nn.Module):
             hit = (key, W, b)
             self._wcache[id(fc)] = hit
         return hit[1], hit[2]
+
+    def _fused_images(self, fc, table):
+        """Operand images of both Linear layers for the one-kernel radial MLP (cached per parameter version)."""
+        l1, l2 = fc[0], fc[-1]
+        key = (l1.weight._version, l1.bias._version, l2.weight._version, l2.bias._version, l2.weight.device)
+        hit = self._fcache.get(id(fc))
+        if hit is None or hit[0] != key:
+            W2, b2 = self._last_linear(fc, table)
+            img1, b1, _ = radial.build_b_images(l1.weight, l1.bias)
+            img2, b2p, nt = radial.build_b_images(W2, b2)
+            hit = (key, img1, b1, img2, b2p, nt)
+            self._fcache[id(fc)] = hit
+        return hit[1:]
+
+    @staticmethod
+    def _fusable(fc, k_in):
+        return (radial.USE_TENSOR_CORES and len(fc) == 4 and isinstance(fc[1], nn.ReLU) and isinstance(fc[0], nn.Linear)
+                and isinstance(fc[3], nn.Linear) and fc[0].out_features <= radial.MAX_K and k_in <= radial.MAX_K)
+
+    def _edge_weights_fused(self, fc, table, ea, node, ns, tgt32, src32):
+        """Per-edge TP weights from the raw pieces: [ea | node[tgt,:ns] | node[src,:ns]] -> Linear -> ReLU -> Linear, all
+        inside ddb200_radial_mlp (split-bf16 tcgen05 GEMMs; no concatenated edge_attr_, no hidden tensor in HBM)."""
+        img1, b1, img2, b2p, nt = self._fused_images(fc, table)
+        return radial.radial_mlp(ea, node, ns, tgt32, src32, img1, b1, fc[0].out_features, img2, b2p, nt)
 
     def _edge_weights(self, fc, table, edge_attr):
         """Radial MLP -> per-edge tensor-product weights [E, >= weight_numel_padded] in the kernel's row layout.
@@ -176,10 +201,12 @@ class TensorProductConvLayer(nn.Module):
     # -- forward -------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0,
-                edge_vec=None, assume_sorted=False):
-        """Reference signature (models/tensor_layers.py:309) plus two optional extensions:
+                edge_vec=None, assume_sorted=False, gather_scalars=0):
+        """Reference signature (models/tensor_layers.py:309) plus optional extensions:
         ``edge_vec`` [E,3]: evaluate the spherical harmonics in-kernel from the edge vectors (``edge_sh`` is ignored);
-        ``assume_sorted``: every edge group is already sorted by target node ``edge_index[0]``."""
+        ``assume_sorted``: every edge group is already sorted by target node ``edge_index[0]``;
+        ``gather_scalars`` = ns > 0: ``edge_attr`` holds only the per-edge part and the radial-MLP kernel appends
+        ``node_attr[edge_index[0], :ns]`` and ``node_attr[edge_index[1], :ns]`` itself (models/cg_model.py:342-349)."""
         if self.training:
             raise RuntimeError("diffdock_b200 layers are inference-only: call .eval()")
         if edge_index.shape[1] == 0 and node_attr.shape[0] == 0:
@@ -233,9 +260,17 @@ class TensorProductConvLayer(nn.Module):
                     ew = ew[order]
             tgt32, src32 = tgt.to(torch.int32).contiguous(), src.to(torch.int32).contiguous()
             geo = geo.contiguous()
+            k_in = ea.shape[1] + 2 * gather_scalars
+            fused = self._fusable(fc, k_in) and (e - s) >= 64
+            if gather_scalars and not fused:     # library path needs the concatenated attributes
+                ea = torch.cat([ea, x[tgt, :gather_scalars], x[src, :gather_scalars]], -1)
             for b0 in range(0, e - s, blk):
                 b1 = min(e - s, b0 + blk)
-                w = self._edge_weights(fc, table, ea[b0:b1].float())
+                if fused:
+                    w = self._edge_weights_fused(fc, table, ea[b0:b1].float(), x, gather_scalars, tgt32[b0:b1],
+                                                 src32[b0:b1])
+                else:
+                    w = self._edge_weights(fc, table, ea[b0:b1].float())
                 if ew_scalar != 1.0:
                     w = w * ew_scalar
                 ops.tpconv_accumulate(handle, x, src32[b0:b1], tgt32[b0:b1], geo[b0:b1], w, sum_buf, cnt_buf,

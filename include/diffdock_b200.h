@@ -126,6 +126,20 @@ int ddb200_pose_update(const float* pos, int64_t n_poses, int n_atoms, int n_bon
 int ddb200_radial_gemm(const float* h, int64_t ldh, int64_t n_edges, int K, const void* b_images, const float* bias,
                        int n_tiles_n, float* out, int64_t ldo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Whole radial MLP of one edge group in one kernel (FCBlock with two Linear layers and ReLU):
+ *   a[e, :] = [edge_attr[e, :ne] | node[tgt[e], :ns] | node[src[e], :ns]]            (the torch.cat / gathers of
+ *                                                                                    models/cg_model.py:342-349; ns = 0: none)
+ *   h       = relu(a @ W1^T + b1)            (hidden units, also a split-bf16 tcgen05 GEMM, kept on chip)
+ *   out     = h @ W2^T + b2                  (as ddb200_radial_gemm)
+ * w1_images: build_b_images(W1 [hidden, ne + 2 ns]) (one N tile), w2_images / b2 / n_tiles_n / out / ldo as above.
+ * Replaces: models/layers.py:10-17 (FCBlock, tp_weights_layers == 2) and the edge_attr_ assembly feeding it.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_radial_mlp(const float* edge_attr, int64_t ld_ea, int ne, const float* node, int64_t ld_node, int ns,
+                      const int32_t* tgt, const int32_t* src, const void* w1_images, const float* b1, int hidden,
+                      const void* w2_images, const float* b2, int n_tiles_n, int64_t n_edges, float* out, int64_t ldo,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
