@@ -27,6 +27,8 @@ SIGNATURES = {
     'ddb200_radial_gemm': (_int, [_vp, _i64, _i64, _int, _vp, _vp, _int, _vp, _i64, _vp]),
     'ddb200_radial_mlp': (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _i64, _vp,
                                  _i64, _vp]),
+    'ddb200_fused_conv': (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp,
+                                 _int, _vp, _i64, _vp, _vp, _int, _i64, _vp, _int, _vp, _vp]),
 }
 
 

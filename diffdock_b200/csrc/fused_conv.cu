@@ -1,0 +1,462 @@
+// Fully fused equivariant convolution for one edge group (sm_100a): radial MLP on tcgen05 + tensor-product contraction
+// straight out of tensor memory + scatter - the per-edge weight tensor [E, weight_numel] never exists in HBM.
+//
+//   for a tile of 128 CSR-sorted edges (one CTA, persistent over tiles):
+//     A0' = split-bf16([edge_attr | node[tgt,:ns] | node[src,:ns] | 1 1])      built in shared memory (128B swizzle)
+//     H   = relu(A0' x W1'^T)          tcgen05.mma -> TMEM -> registers -> A' image (bias folded via the ones columns)
+//     for every N tile (whole rows u of one path block [mul_in, mul_out], <= 256 columns):
+//        Wt = A' x W2'^T[tile]         tcgen05.mma into one of two TMEM accumulators   (B' images streamed by TMA bulk copies)
+//        consumer thread e (= TMEM lane): acc[w,k] += Wt[e, (u,w)] * z_e[u,k],   z_e[u,k] = sum_i x[src_e][u,i] M_e[i,k],
+//                                         M_e = edge_weight * coef * C . Y(vec_e)       (tcgen05.ld 32x32b.x32 + FFMA)
+//     at the end of an output irrep: sum[tgt_e, irrep] += acc  (warp pre-reduction when the 32 lanes share the target)
+//
+// Replaces models/tensor_layers.py:139-144 / :204-221 *including* the FCBlock at :140/:211 and the edge_attr_ assembly of
+// models/cg_model.py:342-349.  Plan (tiles, operand images, CG terms) is built by diffdock_b200/fused.py.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "../../include/diffdock_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;       // CTA tile; BK bf16 = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int A_KB_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;       // 32 KB
+constexpr int MAX_KB = 7;                        // K' <= 448 (K <= 149)
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// multicast variant: one L2 read lands in the same shared-memory offset of every CTA of the cluster in cta_mask, and
+// performs complete_tx on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+__device__ __forceinline__ void put_a(unsigned char* sA, int r, int col, __nv_bfloat16 v) {
+  const int kb = col >> 6, c = (col & 63) >> 3, j = col & 7;
+  *reinterpret_cast<__nv_bfloat16*>(sA + (size_t)kb * A_KB_BYTES + r * 128 + ((c ^ (r & 7)) << 4) + j * 2) = v;
+}
+
+struct FusedParams {
+  const float* ea; long long ld_ea; int ne;          // per-edge attributes
+  const float* node; long long ld_node; int ns;      // node scalars for the radial MLP (both end points)
+  const int* tgt; const int* src;                    // scatter target / gathered node of every edge
+  const __nv_bfloat16* w1img; int K1, n_kb1, H, n_kb;
+  const __nv_bfloat16* w2img;                        // [n_tiles][n_kb][256][64]
+  const int* tiles; int n_tiles;                     // [n_tiles][8]: kind, N_mma, x_off, rows, d_in, out_off, flags, ment_off
+  const int* ment; const int* term_y; const float* term_v; int n_ment, n_terms;
+  const float* x; long long ld_x;                    // node irreps gathered by src
+  const float* vec; const float* ew; int lmax;
+  float* sum; int d_out; float* cnt;
+  long long n_edges;
+};
+
+constexpr int MAX_TILES = 160, MAX_MENT = 256, MAX_TERMS = 512;
+
+// ---- consumer: one TMEM accumulator tile (ROWS rows u of a [mul_in, MULOUT] block) times z -> acc -------------------------
+template <int MULOUT, int DOUT, int ROWS>
+__device__ __forceinline__ void consume_tile(uint32_t taddr, const float* __restrict__ z, float* __restrict__ acc) {
+  constexpr int NCOL = MULOUT * ROWS;
+  static_assert(NCOL % 32 == 0 && NCOL <= 256, "tile width");
+#pragma unroll
+  for (int c = 0; c < NCOL / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j, row = col / MULOUT, w = col % MULOUT;     // compile-time after unrolling
+      const float wv = __uint_as_float(v[j]);
+#pragma unroll
+      for (int k = 0; k < DOUT; ++k) acc[w * DOUT + k] = fmaf(wv, z[row * DOUT + k], acc[w * DOUT + k]);
+    }
+  }
+}
+
+// z[r, k] = sum_i x[x_off + r*DIN + i] * M[i, k] for the tile's rows (0 beyond the valid ones)
+template <int DIN, int DOUT, int ROWS>
+__device__ __forceinline__ void make_z(const float* __restrict__ xr, int nrow, const float* __restrict__ M,
+                                       float* __restrict__ z) {
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float xv[DIN];
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) xv[i] = (r < nrow) ? __ldg(xr + r * DIN + i) : 0.f;
+#pragma unroll
+    for (int k = 0; k < DOUT; ++k) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < DIN; ++i) a = fmaf(xv[i], M[i * 3 + k], a);
+      z[r * DOUT + k] = a;
+    }
+  }
+}
+
+template <int MULOUT, int DOUT, int ROWS>
+__device__ __forceinline__ void tile_body(uint32_t taddr, const float* xr, int nrow, int d_in, const float* M, float* acc) {
+  float z[ROWS * DOUT];
+  if (d_in == 1) make_z<1, DOUT, ROWS>(xr, nrow, M, z);
+  else make_z<3, DOUT, ROWS>(xr, nrow, M, z);
+  consume_tile<MULOUT, DOUT, ROWS>(taddr, z, acc);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int n_kb_max = p.n_kb > p.n_kb1 ? p.n_kb : p.n_kb1;
+  unsigned char* sA = smem;                                      // n_kb_max x 16 KB
+  unsigned char* sB = smem + (size_t)n_kb_max * A_KB_BYTES;      // 3 x 32 KB ring
+  float* sY = reinterpret_cast<float*>(sB + STAGES * B_STAGE_BYTES);   // [9][128] spherical harmonics per consumer thread
+  int* sTiles = reinterpret_cast<int*>(sY + 9 * 128);            // [MAX_TILES][8]
+  int* sMent = sTiles + MAX_TILES * 8;                           // [MAX_MENT][2]
+  int* sTermY = sMent + MAX_MENT * 2;                            // [MAX_TERMS]
+  float* sTermV = reinterpret_cast<float*>(sTermY + MAX_TERMS);  // [MAX_TERMS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTermV + MAX_TERMS);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* a_ready = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < p.n_tiles * 8; i += THREADS) sTiles[i] = p.tiles[i];
+  for (int i = tid; i < p.n_ment * 2; i += THREADS) sMent[i] = p.ment[i];
+  for (int i = tid; i < p.n_terms; i += THREADS) { sTermY[i] = p.term_y[i]; sTermV[i] = p.term_v[i]; }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    mbar_init(a_ready, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);   // | (N >> 3) << 17 per tile
+  const int n1 = ((p.H + 15) / 16) * 16;
+
+  const long long n_mtiles = (p.n_edges + BM - 1) / BM;
+  uint32_t pc = 0, mc = 0, ma = 0, ea = 0, mtc = 0;
+  const __nv_bfloat16 one = __float2bfloat16(1.0f), zero = __float2bfloat16(0.f);
+
+  for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+    __syncthreads();
+    // ---- A0' image: [hi | hi | lo | 1 1 | 0..] of [edge_attr | node[tgt,:ns] | node[src,:ns]] -----------------------
+    {
+      const long long e0 = mt * BM;
+      const int Kin = p.K1, kpad = p.n_kb1 * BK;
+      for (int idx = tid; idx < BM * (kpad - 3 * Kin); idx += THREADS) {
+        const int r = idx / (kpad - 3 * Kin), off = idx % (kpad - 3 * Kin);
+        put_a(sA, r, 3 * Kin + off, off < 2 ? one : zero);
+      }
+      for (int idx = tid; idx < BM * Kin; idx += THREADS) {
+        const int r = idx / Kin, k = idx - r * Kin;
+        const long long e = e0 + r;
+        float v = 0.f;
+        if (e < p.n_edges) {
+          if (k < p.ne) v = __ldg(p.ea + e * p.ld_ea + k);
+          else if (k < p.ne + p.ns) v = __ldg(p.node + (long long)__ldg(p.tgt + e) * p.ld_node + (k - p.ne));
+          else v = __ldg(p.node + (long long)__ldg(p.src + e) * p.ld_node + (k - p.ne - p.ns));
+        }
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+        put_a(sA, r, k, hi);
+        put_a(sA, r, Kin + k, hi);
+        put_a(sA, r, 2 * Kin + k, lo);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+      // ===== operand-B producer: W1' images, then one image set per N tile ====================================
+      if (lane == 0) {
+        const int total = p.n_kb1 + p.n_tiles * p.n_kb;
+        for (int i = 0; i < total; ++i, ++pc) {
+          const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], B_STAGE_BYTES);
+          const unsigned char* src = (i < p.n_kb1)
+              ? reinterpret_cast<const unsigned char*>(p.w1img) + (size_t)i * B_STAGE_BYTES
+              : reinterpret_cast<const unsigned char*>(p.w2img) + (size_t)(i - p.n_kb1) * B_STAGE_BYTES;
+          bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s]);
+        }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer ======================================================================================
+      if (lane == 0) {
+        for (int t = -1; t < p.n_tiles; ++t, ++ma) {
+          const uint32_t buf = ma & 1, aph = (ma >> 1) & 1;
+          mbar_wait(&tempty[buf], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + buf * BN;
+          const int nkb = (t < 0) ? p.n_kb1 : p.n_kb;
+          const int nmma = (t < 0) ? n1 : sTiles[t * 8 + 1];
+          const uint32_t idesc = idesc0 | ((uint32_t)(nmma >> 3) << 17);
+          for (int kb = 0; kb < nkb; ++kb, ++mc) {
+            const uint32_t s = mc % STAGES, ph = (mc / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA + (size_t)kb * A_KB_BYTES), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_bf16(d, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kb | kk) != 0);
+            umma_commit(&empty[s]);
+          }
+          umma_commit(&tfull[buf]);
+          if (t < 0) {          // hidden layer done: wait until the consumers have rewritten the operand image as A'
+            mbar_wait(a_ready, mtc & 1);
+            tc_fence_after();
+          }
+        }
+      }
+    } else if (warp >= 4) {
+      // ===== consumers: thread <-> edge <-> TMEM lane ===========================================================
+      const int q = warp & 3, ct = q * 32 + lane;          // row of the edge tile
+      const long long e = mt * BM + ct;
+      const bool valid = e < p.n_edges;
+      const int src_e = valid ? __ldg(p.src + e) : 0, dst_e = valid ? __ldg(p.tgt + e) : -1;
+      const float ew_e = (valid && p.ew) ? __ldg(p.ew + e) : 1.f;
+      {   // real spherical harmonics of the edge vector, component normalisation (e3nn polynomials)
+        float vx = valid ? __ldg(p.vec + 3 * e) : 1.f, vy = valid ? __ldg(p.vec + 3 * e + 1) : 0.f,
+              vz = valid ? __ldg(p.vec + 3 * e + 2) : 0.f;
+        const float nrm = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
+        vx /= nrm; vy /= nrm; vz /= nrm;
+        const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f, s15 = 3.872983346207417f;
+        sY[0 * 128 + ct] = 1.f;
+        sY[1 * 128 + ct] = s3 * vx; sY[2 * 128 + ct] = s3 * vy; sY[3 * 128 + ct] = s3 * vz;
+        sY[4 * 128 + ct] = s15 * vx * vz;
+        sY[5 * 128 + ct] = s15 * vx * vy;
+        sY[6 * 128 + ct] = s5 * (vy * vy - 0.5f * (vx * vx + vz * vz));
+        sY[7 * 128 + ct] = s15 * vy * vz;
+        sY[8 * 128 + ct] = 0.5f * s15 * (vz * vz - vx * vx);
+      }
+      const float* xrow = p.x + (long long)src_e * p.ld_x;
+      {   // hidden activations: ReLU (bias already folded), bf16 split, written back over the operand image as A'
+        const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
+        mbar_wait(&tfull[buf], aph);
+        tc_fence_after();
+        const int K = p.H, kpad = p.n_kb * BK;
+        for (int c0 = 0; c0 < K; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int k = c0 + j;
+            if (k < K) {
+              const float hval = fmaxf(__uint_as_float(v[j]), 0.f);
+              const __nv_bfloat16 hi = __float2bfloat16(hval);
+              const __nv_bfloat16 lo = __float2bfloat16(hval - __bfloat162float(hi));
+              put_a(sA, ct, k, hi);
+              put_a(sA, ct, K + k, hi);
+              put_a(sA, ct, 2 * K + k, lo);
+            }
+          }
+        }
+        for (int col = 3 * K; col < kpad; ++col) put_a(sA, ct, col, col < 3 * K + 2 ? one : zero);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&tempty[buf]); mbar_arrive(a_ready); }
+        ++ea;
+      }
+      float acc[48];
+      for (int t = 0; t < p.n_tiles; ++t, ++ea) {
+        const int* ti = sTiles + t * 8;
+        const int kind = ti[0], x_off = ti[2], nrow = ti[3], d_in = ti[4], out_off = ti[5], flags = ti[6];
+        if (flags & 1) {
+#pragma unroll
+          for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+        }
+        // M[i,k] = edge_weight * sum_j coef*C[i,j,k] * Y[j]  (at most 3x3 for the supported paths; row-major, stride 3)
+        float M[9];
+        {
+          const int dout = (kind == 0 || kind == 2) ? 1 : 3;
+          const int* me = sMent + ti[7] * 2;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              float a = 0.f;
+              if (i < d_in && k < dout) {
+                const int b = me[(i * dout + k) * 2], n = me[(i * dout + k) * 2 + 1];
+                for (int tq = b; tq < b + n; ++tq) a = fmaf(sTermV[tq], sY[sTermY[tq] * 128 + ct], a);
+              }
+              M[i * 3 + k] = a * ew_e;
+            }
+        }
+        const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
+        mbar_wait(&tfull[buf], aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+        const float* xr = xrow + x_off;
+        switch (kind) {
+          case 0: tile_body<48, 1, 4>(taddr, xr, nrow, d_in, M, acc); break;
+          case 1: tile_body<10, 3, 16>(taddr, xr, nrow, d_in, M, acc); break;
+          case 2: tile_body<16, 1, 16>(taddr, xr, nrow, d_in, M, acc); break;
+          default: tile_body<4, 3, 16>(taddr, xr, nrow, d_in, M, acc); break;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (flags & 2) {   // end of an output irrep: scatter-add (pre-reduced over the warp when all lanes share the target)
+          const int nacc = (kind == 0) ? 48 : (kind == 1 ? 30 : (kind == 2 ? 16 : 12));
+          const int d0 = __shfl_sync(0xffffffffu, dst_e, 0);
+          const bool uniform = __all_sync(0xffffffffu, dst_e == d0) && d0 >= 0;
+          if (uniform) {
+#pragma unroll
+            for (int i = 0; i < 48; ++i) {
+              if (i < nacc) {
+                float v = acc[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == (i & 31)) atomicAdd(p.sum + (long long)d0 * p.d_out + out_off + i, v);
+              }
+            }
+          } else if (valid) {
+            float* srow = p.sum + (long long)dst_e * p.d_out + out_off;
+#pragma unroll
+            for (int i = 0; i < 48; ++i)
+              if (i < nacc) atomicAdd(srow + i, acc[i]);
+          }
+        }
+      }
+      if (p.cnt && valid) atomicAdd(p.cnt + dst_e, 1.f);
+    }
+    ++mtc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace
+
+extern "C" int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, const float* node, int64_t ld_node, int ns,
+                                 const int32_t* tgt, const int32_t* src, const void* w1_images, int hidden,
+                                 const void* w2_images, const int32_t* tiles, int n_tiles, const int32_t* ment, int n_ment,
+                                 const int32_t* term_y, const float* term_v, int n_terms, const float* x, int64_t ld_x,
+                                 const float* edge_vec, const float* edge_weight, int sh_lmax, int64_t n_edges,
+                                 float* sum, int d_out, float* cnt, void* stream) {
+  if (!edge_attr || !w1_images || !w2_images || !tiles || !ment || !term_y || !term_v || !x || !edge_vec || !sum ||
+      !tgt || !src || n_edges < 0 || ne <= 0 || ns < 0 || hidden <= 0 || n_tiles <= 0 || d_out <= 0)
+    return DDB200_EINVAL;
+  if (ns > 0 && (!node || ld_node < ns)) return DDB200_EINVAL;
+  if (n_tiles > MAX_TILES || n_ment > MAX_MENT || n_terms > MAX_TERMS || sh_lmax < 0 || sh_lmax > 2) return DDB200_EINVAL;
+  const int K1 = ne + 2 * ns;
+  const int n_kb = (3 * hidden + 2 + BK - 1) / BK, n_kb1 = (3 * K1 + 2 + BK - 1) / BK;
+  if (n_kb > MAX_KB || n_kb1 > MAX_KB || hidden > BN) return DDB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(w1_images) & 127) || (reinterpret_cast<uintptr_t>(w2_images) & 127)) return DDB200_EINVAL;
+  if (n_edges == 0) return 0;
+  FusedParams p = {};
+  p.ea = edge_attr; p.ld_ea = ld_ea; p.ne = ne; p.node = node; p.ld_node = ld_node; p.ns = ns; p.tgt = tgt; p.src = src;
+  p.w1img = reinterpret_cast<const __nv_bfloat16*>(w1_images); p.K1 = K1; p.n_kb1 = n_kb1; p.H = hidden; p.n_kb = n_kb;
+  p.w2img = reinterpret_cast<const __nv_bfloat16*>(w2_images); p.tiles = tiles; p.n_tiles = n_tiles;
+  p.ment = ment; p.term_y = term_y; p.term_v = term_v; p.n_ment = n_ment; p.n_terms = n_terms;
+  p.x = x; p.ld_x = ld_x; p.vec = edge_vec; p.ew = edge_weight; p.lmax = sh_lmax; p.sum = sum; p.d_out = d_out; p.cnt = cnt;
+  p.n_edges = n_edges;
+  const int n_kb_max = n_kb > n_kb1 ? n_kb : n_kb1;
+  const size_t smem = (size_t)n_kb_max * A_KB_BYTES + STAGES * B_STAGE_BYTES + 9 * 128 * 4 + MAX_TILES * 8 * 4 +
+                      MAX_MENT * 2 * 4 + MAX_TERMS * 8 + 16 * sizeof(uint64_t) + 1024;
+  if (smem > 227 * 1024) return DDB200_ESMEM;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(fused_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_mtiles = (n_edges + BM - 1) / BM;
+  const unsigned grid = (unsigned)(n_mtiles < sms ? n_mtiles : sms);
+  fused_conv_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}

@@ -11,7 +11,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import ops, radial
+from . import fused, ops, radial
 from .irreps import irreps_dim, parse_irreps
 from .tp_table import build_table
 
@@ -136,6 +136,7 @@ class TensorProductConvLayer(nn.Module):
         self._wcache = {}
         self._gcache = {}
         self._fcache = {}
+        self._pcache = {}
 
     # -- radial MLP -> per-edge weights in kernel layout ------------------------------------------------------
     def _last_linear(self, fc, table):
@@ -167,6 +168,18 @@ class TensorProductConvLayer(nn.Module):
             hit = (key, img1, b1, img2, b2p, nt)
             self._fcache[id(fc)] = hit
         return hit[1:]
+
+    def _fused_plan(self, fc, table, k_in):
+        """Plan of the fully fused kernel for this radial MLP, or None when the shapes are outside its templates."""
+        if not (fused.ENABLED and self._fusable(fc, k_in) and fused.supported(table, fc[0].out_features, k_in)):
+            return None
+        l1, l2 = fc[0], fc[-1]
+        key = (l1.weight._version, l1.bias._version, l2.weight._version, l2.bias._version, l2.weight.device)
+        hit = self._pcache.get(id(fc))
+        if hit is None or hit[0] != key:
+            hit = (key, fused.FusedPlan(table, l1.weight, l1.bias, l2.weight, l2.bias))
+            self._pcache[id(fc)] = hit
+        return hit[1]
 
     @staticmethod
     def _fusable(fc, k_in):
@@ -261,12 +274,18 @@ class TensorProductConvLayer(nn.Module):
             tgt32, src32 = tgt.to(torch.int32).contiguous(), src.to(torch.int32).contiguous()
             geo = geo.contiguous()
             k_in = ea.shape[1] + 2 * gather_scalars
-            fused = self._fusable(fc, k_in) and (e - s) >= 64
-            if gather_scalars and not fused:     # library path needs the concatenated attributes
+            plan = self._fused_plan(fc, table, k_in) if (from_vec and ew_scalar == 1.0 and (e - s) >= 64) else None
+            if plan is not None:      # radial MLP + tensor product + scatter in one kernel, no per-edge weights in HBM
+                fused.fused_conv(plan, ea.float(), x, gather_scalars, tgt32, src32, x, geo, sum_buf, cnt_buf,
+                                 edge_weight=ew)
+                s = e
+                continue
+            mlp_fused = self._fusable(fc, k_in) and (e - s) >= 64
+            if gather_scalars and not mlp_fused:     # library path needs the concatenated attributes
                 ea = torch.cat([ea, x[tgt, :gather_scalars], x[src, :gather_scalars]], -1)
             for b0 in range(0, e - s, blk):
                 b1 = min(e - s, b0 + blk)
-                if fused:
+                if mlp_fused:
                     w = self._edge_weights_fused(fc, table, ea[b0:b1].float(), x, gather_scalars, tgt32[b0:b1],
                                                  src32[b0:b1])
                 else:

@@ -140,6 +140,24 @@ int ddb200_radial_mlp(const float* edge_attr, int64_t ld_ea, int ne, const float
                       const void* w2_images, const float* b2, int n_tiles_n, int64_t n_edges, float* out, int64_t ldo,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fully fused convolution of one edge group: radial MLP (as ddb200_radial_mlp) whose output tiles are contracted with the
+ * edge irreps straight out of tensor memory and scatter-added - the [E, weight_numel] weights never reach HBM.
+ *   sum[tgt[e], :] += TP(x[src[e], :], Y(edge_vec[e]), FCBlock([edge_attr[e] | node[tgt[e],:ns] | node[src[e],:ns]])) * edge_weight[e]
+ *   cnt[tgt[e]]    += 1
+ * w1_images / w2_images / tiles / ment / term_y / term_v: the plan built by diffdock_b200/fused.py (operand images with the
+ * biases folded in, N tiles = whole rows of one path block, Clebsch-Gordan terms).  Supported shapes:
+ * (mul_out, 2l_out+1) in {(48,1),(10,3),(16,1),(4,3)}, l_in <= 1, spherical harmonics from edge vectors (sh_lmax <= 2).
+ * Replaces: models/tensor_layers.py:139-144 / :204-221 including fc_layer(edge_attr) and the edge_attr_ assembly of
+ * models/cg_model.py:342-349.  Follow with ddb200_tpconv_finalize.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, const float* node, int64_t ld_node, int ns,
+                      const int32_t* tgt, const int32_t* src, const void* w1_images, int hidden, const void* w2_images,
+                      const int32_t* tiles, int n_tiles, const int32_t* ment, int n_ment, const int32_t* term_y,
+                      const float* term_v, int n_terms, const float* x, int64_t ld_x, const float* edge_vec,
+                      const float* edge_weight, int sh_lmax, int64_t n_edges, float* sum, int d_out, float* cnt,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

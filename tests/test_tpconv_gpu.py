@@ -38,3 +38,18 @@ def test_skewed_degrees_and_empty_rows(built_lib):
 def test_small_config(built_lib):
     assert layer_parity_case(seed=3, ns=16, nv=4, stage=3) < TOL
     assert layer_parity_case(seed=4, ns=24, nv=6, stage=2, lmax=1, faster=True) < TOL
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2, 3])
+def test_fully_fused_conv_matches_oracle(built_lib, stage):
+    """csrc/fused_conv.cu (radial MLP on tcgen05 + contraction out of TMEM + scatter, one kernel) vs the oracle layer.
+    Tolerance 1e-4: two chained split-bf16 GEMMs feed the contraction."""
+    from diffdock_b200 import fused
+    assert fused.ENABLED
+    assert layer_parity_case(seed=20 + stage, stage=stage, lmax=2, n_nodes=300, n_edges=4000, groups=1) < 1e-4
+    assert layer_parity_case(seed=30 + stage, stage=stage, lmax=1, faster=True, n_nodes=50, n_edges=777, groups=2) < 1e-4
+
+
+def test_fused_conv_skewed_and_unsorted_edges(built_lib):
+    assert layer_parity_case(seed=41, stage=3, n_nodes=40, n_edges=5000, groups=4, edge_weight_tensor=True) < 1e-4
+    assert layer_parity_case(seed=42, stage=3, n_nodes=3000, n_edges=200) < 1e-4
