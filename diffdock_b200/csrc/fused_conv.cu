@@ -117,6 +117,26 @@ __device__ __forceinline__ void put_a(unsigned char* sA, int r, int col, __nv_bf
   *reinterpret_cast<__nv_bfloat16*>(sA + (size_t)kb * A_KB_BYTES + r * 128 + ((c ^ (r & 7)) << 4) + j * 2) = v;
 }
 
+// 8 consecutive columns col0..col0+7 (col0 % 8 == 0) of row r = one 16-byte chunk of the swizzled image
+__device__ __forceinline__ void put_a8(unsigned char* sA, int r, int col0, const uint4& v) {
+  const int kb = col0 >> 6, c = (col0 & 63) >> 3;
+  *reinterpret_cast<uint4*>(sA + (size_t)kb * A_KB_BYTES + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+}
+// split 8 floats into bf16 hi / lo parts, packed as two 16-byte chunks
+__device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16(f[2 * i]), h1 = __float2bfloat16(f[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16(f[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16(f[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 struct FusedParams {
   const float* ea; long long ld_ea; int ne;          // per-edge attributes
   const float* node; long long ld_node; int ns;      // node scalars for the radial MLP (both end points)
@@ -171,11 +191,16 @@ __device__ __forceinline__ void make_z(const float* __restrict__ xr, int nrow, c
   }
 }
 
+// z (global loads of the gathered node row + tiny matrix products) is formed BEFORE waiting for the accumulator, so that
+// its latency overlaps the tile's MMAs
 template <int MULOUT, int DOUT, int ROWS>
-__device__ __forceinline__ void tile_body(uint32_t taddr, const float* xr, int nrow, int d_in, const float* M, float* acc) {
+__device__ __forceinline__ void tile_body(uint32_t taddr, const float* xr, int nrow, int d_in, const float* M, float* acc,
+                                          uint64_t* tfull_bar, uint32_t parity) {
   float z[ROWS * DOUT];
   if (d_in == 1) make_z<1, DOUT, ROWS>(xr, nrow, M, z);
   else make_z<3, DOUT, ROWS>(xr, nrow, M, z);
+  mbar_wait(tfull_bar, parity);
+  tc_fence_after();
   consume_tile<MULOUT, DOUT, ROWS>(taddr, z, acc);
 }
 
@@ -234,6 +259,45 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         const int r = idx / (kpad - 3 * Kin), off = idx % (kpad - 3 * Kin);
         put_a(sA, r, 3 * Kin + off, off < 2 ? one : zero);
       }
+      if (((p.ne | p.ns) & 7) == 0 && ((p.ld_ea | p.ld_node) & 3) == 0) {
+        // vector path: one work item = 8 consecutive input columns of one edge = two independent 16-byte loads, three
+        // 16-byte shared stores; all of a thread's loads are issued before the first conversion
+        const int groups = Kin >> 3, items = BM * groups;
+        constexpr int PER = 4;
+        for (int base = tid; base < items; base += THREADS * PER) {
+          float4 f[PER][2];
+          int rr[PER], gg[PER];
+#pragma unroll
+          for (int u = 0; u < PER; ++u) {
+            const int idx = base + u * THREADS;
+            f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[u] = -1;
+            if (idx < items) {
+              const int r = idx / groups, g = idx - r * groups, k = g << 3;
+              rr[u] = r; gg[u] = g;
+              const long long e = e0 + r;
+              if (e < p.n_edges) {
+                const float* srcp;
+                if (k < p.ne) srcp = p.ea + e * p.ld_ea + k;
+                else if (k < p.ne + p.ns) srcp = p.node + (long long)__ldg(p.tgt + e) * p.ld_node + (k - p.ne);
+                else srcp = p.node + (long long)__ldg(p.src + e) * p.ld_node + (k - p.ne - p.ns);
+                f[u][0] = __ldg(reinterpret_cast<const float4*>(srcp));
+                f[u][1] = __ldg(reinterpret_cast<const float4*>(srcp) + 1);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < PER; ++u) {
+            if (rr[u] >= 0) {
+              uint4 hi, lo;
+              split8(reinterpret_cast<const float*>(&f[u][0]), hi, lo);
+              put_a8(sA, rr[u], gg[u] << 3, hi);
+              put_a8(sA, rr[u], Kin + (gg[u] << 3), hi);
+              put_a8(sA, rr[u], 2 * Kin + (gg[u] << 3), lo);
+            }
+          }
+        }
+      } else
       for (int idx = tid; idx < BM * Kin; idx += THREADS) {
         const int r = idx / Kin, k = idx - r * Kin;
         const long long e = e0 + r;
@@ -260,11 +324,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         for (int i = 0; i < total; ++i, ++pc) {
           const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], B_STAGE_BYTES);
+          // only the rows the MMA reads (N of the tile) are fetched: images are row-major [256][128 B]
+          const int rows = (i < p.n_kb1) ? n1 : sTiles[((i - p.n_kb1) / p.n_kb) * 8 + 1];
+          const uint32_t bytes = (uint32_t)rows * 128u;
+          mbar_expect_tx(&full[s], bytes);
           const unsigned char* src = (i < p.n_kb1)
               ? reinterpret_cast<const unsigned char*>(p.w1img) + (size_t)i * B_STAGE_BYTES
               : reinterpret_cast<const unsigned char*>(p.w2img) + (size_t)(i - p.n_kb1) * B_STAGE_BYTES;
-          bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s]);
+          bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, bytes, &full[s]);
         }
       }
     } else if (warp == 1) {
@@ -325,16 +392,33 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         for (int c0 = 0; c0 < K; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
+          if ((K & 7) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int k = c0 + j;
-            if (k < K) {
-              const float hval = fmaxf(__uint_as_float(v[j]), 0.f);
-              const __nv_bfloat16 hi = __float2bfloat16(hval);
-              const __nv_bfloat16 lo = __float2bfloat16(hval - __bfloat162float(hi));
-              put_a(sA, ct, k, hi);
-              put_a(sA, ct, K + k, hi);
-              put_a(sA, ct, 2 * K + k, lo);
+            for (int g = 0; g < 4; ++g) {
+              const int k = c0 + 8 * g;
+              if (k < K) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[8 * g + j]), 0.f);
+                uint4 hi, lo;
+                split8(f, hi, lo);
+                put_a8(sA, ct, k, hi);
+                put_a8(sA, ct, K + k, hi);
+                put_a8(sA, ct, 2 * K + k, lo);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int k = c0 + j;
+              if (k < K) {
+                const float hval = fmaxf(__uint_as_float(v[j]), 0.f);
+                const __nv_bfloat16 hi = __float2bfloat16(hval);
+                const __nv_bfloat16 lo = __float2bfloat16(hval - __bfloat162float(hi));
+                put_a(sA, ct, k, hi);
+                put_a(sA, ct, K + k, hi);
+                put_a(sA, ct, 2 * K + k, lo);
+              }
             }
           }
         }
@@ -371,15 +455,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
             }
         }
         const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
-        mbar_wait(&tfull[buf], aph);
-        tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         const float* xr = xrow + x_off;
         switch (kind) {
-          case 0: tile_body<48, 1, 4>(taddr, xr, nrow, d_in, M, acc); break;
-          case 1: tile_body<10, 3, 16>(taddr, xr, nrow, d_in, M, acc); break;
-          case 2: tile_body<16, 1, 16>(taddr, xr, nrow, d_in, M, acc); break;
-          default: tile_body<4, 3, 16>(taddr, xr, nrow, d_in, M, acc); break;
+          case 0: tile_body<48, 1, 4>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
+          case 1: tile_body<10, 3, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
+          case 2: tile_body<16, 1, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
+          default: tile_body<4, 3, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
         }
         tc_fence_before();
         __syncwarp();

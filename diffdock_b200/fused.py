@@ -127,6 +127,10 @@ class FusedPlan:
         self.term_v = torch.as_tensor(np.asarray(term_v if term_v else [0.0], dtype=np.float32), device=dev).contiguous()
         self.n_ment = len(ment_i) // 2
         self.n_terms = len(term_y)
+        # bf16 tensor-core FLOPs issued per 128-edge tile (split-bf16 x3, K padded to 64s, full-width N tiles)
+        n_kb, n_kb1 = (3 * H + BK - 1) // BK, (3 * K1 + BK - 1) // BK
+        n1 = (H + 15) // 16 * 16
+        self.mma_flops_per_tile = 2 * 128 * (n1 * n_kb1 * BK + sum(t[1] for t in tiles) * n_kb * BK)
 
 
 def fused_conv(plan: FusedPlan, edge_attr, node, ns, tgt32, src32, x, edge_vec, sum_buf, cnt_buf, edge_weight=None):
@@ -156,5 +160,6 @@ def fused_conv(plan: FusedPlan, edge_attr, node, ns, tgt32, src32, x, edge_vec, 
         PROFILE.fused_pairs.append((e0, e1))
         PROFILE.fused_bytes += E * (4 * t.weight_numel + 12 + 4) + 4 * (sum_buf.shape[0] + 1) + \
             4 * x.shape[0] * t.d_in + 4 * sum_buf.shape[0] * t.d_out
+        PROFILE.fused_flops += ((E + 127) // 128) * plan.mma_flops_per_tile
         PROFILE.all_launches += 1
     _lib.check(rc, 'ddb200_fused_conv')

@@ -34,13 +34,14 @@ class _Profile:
 
     def reset(self, enabled=False):
         self.enabled, self.pairs, self.bytes, self.all_launches = enabled, [], 0, 0
-        self.fused_pairs, self.fused_bytes = [], 0
+        self.fused_pairs, self.fused_bytes, self.fused_flops = [], 0, 0
 
     def summary(self):
         torch.cuda.synchronize()
         return {'launches': len(self.pairs), 'ms': sum(a.elapsed_time(b) for a, b in self.pairs), 'bytes': self.bytes,
                 'all_launches': self.all_launches, 'fused_launches': len(self.fused_pairs),
-                'fused_ms': sum(a.elapsed_time(b) for a, b in self.fused_pairs), 'fused_bytes': self.fused_bytes}
+                'fused_ms': sum(a.elapsed_time(b) for a, b in self.fused_pairs), 'fused_bytes': self.fused_bytes,
+                'fused_flops': self.fused_flops}
 
 
 PROFILE = _Profile()
