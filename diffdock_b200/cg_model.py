@@ -295,27 +295,24 @@ class CGModel(nn.Module):
         n_lig = lig_node.shape[0]
         node = torch.cat([lig_node, rec_node], 0)
         rl_tgt, rev = torch.sort(ri, stable=True)            # receptor <- ligand direction: same pairs, sorted by residue
-        groups = [
-            (ll_tgt, ll_src, ll_ea, ll_vec, ll_ew),                                             # lig <- lig
-            (li, ri + n_lig, lr_ea, lr_vec, lr_ew),                                             # lig <- rec
-            (c['rr_tgt'] + n_lig, c['rr_src'] + n_lig, rr_ea, c['rr_vec'], c['rr_ew']),         # rec <- rec
-            (rl_tgt + n_lig, li[rev], lr_ea[rev], -lr_vec[rev],
-             lr_ew[rev] if torch.is_tensor(lr_ew) else lr_ew),                                  # rec <- lig, SH(-v)
+        i32 = lambda t: t.to(torch.int32).contiguous()
+        ewt = lambda w: w.reshape(-1).contiguous() if torch.is_tensor(w) else None
+        rr_tgt32 = c.setdefault('rr_tgt32', {}).get(n_lig)
+        if rr_tgt32 is None:      # static receptor graph: int32 indices in the joint numbering, once per batch
+            rr_tgt32 = c['rr_tgt32'][n_lig] = (i32(c['rr_tgt'] + n_lig), i32(c['rr_src'] + n_lig))
+        groups = [   # (target, gathered node, edge attr, edge vector, edge weight): int32, CSR-sorted, built once per forward
+            (i32(ll_tgt), i32(ll_src), ll_ea, ll_vec.contiguous(), ewt(ll_ew)),                          # lig <- lig
+            (i32(li), i32(ri + n_lig), lr_ea, lr_vec.contiguous(), ewt(lr_ew)),                          # lig <- rec
+            (rr_tgt32[0], rr_tgt32[1], rr_ea, c['rr_vec'], ewt(c['rr_ew'])),                             # rec <- rec
+            (i32(rl_tgt + n_lig), i32(li[rev]), lr_ea[rev], (-lr_vec[rev]).contiguous(),
+             ewt(lr_ew[rev]) if torch.is_tensor(lr_ew) else None),                                       # rec <- lig, SH(-v)
         ]
-        smooth = self.smooth_edges
         L = len(self.conv_layers)
         for l, layer in enumerate(self.conv_layers):
             use = groups if l < L - 1 else groups[:2]       # last layer: only edges that end on ligand atoms (:347-349)
-            tgt = torch.cat([g[0] for g in use])
-            src = torch.cat([g[1] for g in use])
-            vec = torch.cat([g[3] for g in use])
-            ew = torch.cat([g[4] if torch.is_tensor(g[4]) else torch.ones((g[0].shape[0], 1), device=node.device)
-                            for g in use]) if smooth else 1.0
-            ea = [g[2] for g in use]          # end-point scalars are gathered inside the radial-MLP kernel
-            if not self.differentiate_convolutions:
-                ea = torch.cat(ea, 0)
-            node = layer(node, torch.stack([tgt, src]), ea, None, edge_weight=ew, edge_vec=vec, assume_sorted=True,
-                         gather_scalars=ns)
+            if not self.differentiate_convolutions:         # one radial MLP for all edge types: a single merged group
+                use = [tuple(torch.cat([g[k] for g in use]) if use[0][k] is not None else None for k in range(5))]
+            node = layer.forward_groups(node, use, gather_scalars=ns)
         lig_node = node[:n_lig]
 
         # -- translation / rotation head (:368-395) -----------------------------------------------------------------

@@ -250,41 +250,67 @@ class TensorProductConvLayer(nn.Module):
         assert sum(g.shape[0] for g in groups) == E, "Sum of edge_attr_groups must be equal to edge_index.shape[1]"
 
         from_vec = edge_vec is not None and self.tp.vec_capable
-        handle = self.tp.handle(from_vec)
-        table = handle.table
         geo_all = (edge_vec if from_vec else edge_sh).float()
         ew_all = edge_weight if torch.is_tensor(edge_weight) else None
         ew_scalar = 1.0 if torch.is_tensor(edge_weight) else float(edge_weight)
+        prepared, s = [], 0
+        for ea in groups:
+            e = s + ea.shape[0]
+            if e > s:
+                tgt, src = edge_index[0, s:e], edge_index[1, s:e]
+                geo, ew = geo_all[s:e], (ew_all[s:e].reshape(-1) if ew_all is not None else None)
+                if not assume_sorted:
+                    tgt, order = torch.sort(tgt, stable=True)
+                    src, geo, ea = src[order], geo[order], ea[order]
+                    if ew is not None:
+                        ew = ew[order]
+                prepared.append((tgt.to(torch.int32).contiguous(), src.to(torch.int32).contiguous(), ea, geo.contiguous(), ew))
+            else:
+                prepared.append(None)
+            s = e
+        return self._run(x, prepared, fcs, from_vec, ew_scalar, n_out, reduce, gather_scalars, scale, shift).to(_dtype)
 
+    @torch.no_grad()
+    def forward_groups(self, node_attr, groups, out_nodes=None, reduce='mean', gather_scalars=0):
+        """Fast internal entry (used by diffdock_b200.CGModel): ``groups`` is a list with one item per radial MLP of this
+        layer, each ``(tgt_int32, src_int32, edge_attr, edge_vec, edge_weight | None)`` already CSR-sorted by target, so
+        that no per-layer concatenation / conversion / slicing of the edge arrays is needed."""
+        x = node_attr.float()
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        n_out = int(out_nodes) if out_nodes else x.shape[0]
+        scale, shift = self.batch_norm.fold() if self.batch_norm is not None else (None, None)
+        fcs = [self.fc] * len(groups) if self.edge_groups == 1 else list(self.fc)
+        prepared = [g if (g is not None and g[0].shape[0] > 0) else None for g in groups]
+        if all(g is None for g in prepared):
+            out = torch.zeros((x.shape[0], self.out_size), dtype=torch.float32, device=x.device)
+            if self.residual:
+                out[:, :x.shape[1]] += x
+            return out
+        return self._run(x, prepared, fcs, True, 1.0, n_out, reduce, gather_scalars, scale, shift)
+
+    def _run(self, x, prepared, fcs, from_vec, ew_scalar, n_out, reduce, gather_scalars, scale, shift):
+        handle = self.tp.handle(from_vec)
+        table = handle.table
         sum_buf = torch.zeros((n_out, self.out_size), dtype=torch.float32, device=x.device)
         cnt_buf = torch.zeros((n_out,), dtype=torch.float32, device=x.device)
         blk = max(1024, WEIGHT_BLOCK_BYTES // (4 * table.weight_numel_padded))
-        s = 0
-        for ea, fc in zip(groups, fcs):
-            e = s + ea.shape[0]
-            if e == s:
+        for item, fc in zip(prepared, fcs):
+            if item is None:
                 continue
-            tgt, src = edge_index[0, s:e], edge_index[1, s:e]
-            geo, ew = geo_all[s:e], (ew_all[s:e].reshape(-1) if ew_all is not None else None)
-            if not assume_sorted:
-                tgt, order = torch.sort(tgt, stable=True)
-                src, geo, ea = src[order], geo[order], ea[order]
-                if ew is not None:
-                    ew = ew[order]
-            tgt32, src32 = tgt.to(torch.int32).contiguous(), src.to(torch.int32).contiguous()
-            geo = geo.contiguous()
+            tgt32, src32, ea, geo, ew = item
+            n_e = tgt32.shape[0]
             k_in = ea.shape[1] + 2 * gather_scalars
-            plan = self._fused_plan(fc, table, k_in) if (from_vec and ew_scalar == 1.0 and (e - s) >= 64) else None
+            plan = self._fused_plan(fc, table, k_in) if (from_vec and ew_scalar == 1.0 and n_e >= 64) else None
             if plan is not None:      # radial MLP + tensor product + scatter in one kernel, no per-edge weights in HBM
                 fused.fused_conv(plan, ea.float(), x, gather_scalars, tgt32, src32, x, geo, sum_buf, cnt_buf,
                                  edge_weight=ew)
-                s = e
                 continue
-            mlp_fused = self._fusable(fc, k_in) and (e - s) >= 64
+            mlp_fused = self._fusable(fc, k_in) and n_e >= 64
             if gather_scalars and not mlp_fused:     # library path needs the concatenated attributes
-                ea = torch.cat([ea, x[tgt, :gather_scalars], x[src, :gather_scalars]], -1)
-            for b0 in range(0, e - s, blk):
-                b1 = min(e - s, b0 + blk)
+                ea = torch.cat([ea, x[tgt32.long(), :gather_scalars], x[src32.long(), :gather_scalars]], -1)
+            for b0 in range(0, n_e, blk):
+                b1 = min(n_e, b0 + blk)
                 if mlp_fused:
                     w = self._edge_weights_fused(fc, table, ea[b0:b1].float(), x, gather_scalars, tgt32[b0:b1],
                                                  src32[b0:b1])
@@ -295,10 +321,8 @@ class TensorProductConvLayer(nn.Module):
                 ops.tpconv_accumulate(handle, x, src32[b0:b1], tgt32[b0:b1], geo[b0:b1], w, sum_buf, cnt_buf,
                                       edge_weight=ew[b0:b1] if ew is not None else None, count_node_bytes=b0 == 0)
                 del w
-            s = e
         res = x if self.residual else None
-        out = ops.tpconv_finalize(sum_buf, cnt_buf, reduce == 'mean', scale, shift, res)
-        return out.to(_dtype)
+        return ops.tpconv_finalize(sum_buf, cnt_buf, reduce == 'mean', scale, shift, res)
 
 
 class OldTensorProductConvLayer(nn.Module):
