@@ -161,5 +161,5 @@ def fused_conv(plan: FusedPlan, edge_attr, node, ns, tgt32, src32, x, edge_vec, 
         PROFILE.fused_bytes += E * (4 * t.weight_numel + 12 + 4) + 4 * (sum_buf.shape[0] + 1) + \
             4 * x.shape[0] * t.d_in + 4 * sum_buf.shape[0] * t.d_out
         PROFILE.fused_flops += ((E + 127) // 128) * plan.mma_flops_per_tile
-        PROFILE.all_launches += 1
+    PROFILE.all_launches += 1
     _lib.check(rc, 'ddb200_fused_conv')

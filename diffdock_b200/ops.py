@@ -106,7 +106,7 @@ def tpconv_accumulate(h: TpHandle, x, edge_src, edge_dst, geo, w, sum_buf, cnt_b
         PROFILE.bytes += E * (4 * t.weight_numel + 12 + 4) + (4 * E if edge_weight is not None else 0)
         if count_node_bytes:   # node tensors are compulsory traffic once per (layer, edge set), not per edge block
             PROFILE.bytes += 4 * (sum_buf.shape[0] + 1) + 4 * x.shape[0] * t.d_in + 4 * sum_buf.shape[0] * t.d_out
-        PROFILE.all_launches += 1
+    PROFILE.all_launches += 1
     _lib.check(rc, 'ddb200_tpconv_accumulate')
 
 
