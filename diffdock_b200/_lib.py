@@ -29,6 +29,7 @@ SIGNATURES = {
                                  _i64, _vp]),
     'ddb200_fused_conv': (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp,
                                  _int, _vp, _i64, _vp, _vp, _int, _i64, _vp, _int, _vp, _vp]),
+    'ddb200_fused_debug_read': (_int, [_vp]),
 }
 
 

@@ -22,9 +22,15 @@
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;       // CTA tile; BK bf16 = one 128-byte swizzle row
-constexpr int STAGES = 3;
 constexpr int A_KB_BYTES = BM * BK * 2;          // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;       // 32 KB
+constexpr int B_IMAGE_BYTES = BN * BK * 2;       // 32 KB: one k-block image of an N tile in global memory
+// CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 a CTA pair works on 256 edges, each CTA stages only its half of the
+// rows of every B image (half the L2->smem traffic and half the B reads per SM), so the ring can be deeper.
+constexpr int MAX_N = 192;                       // widest N tile of a plan (and widest hidden layer)
+template <int CG> struct Ring {
+  static constexpr int STAGES = 4 * CG;
+  static constexpr int STAGE_BYTES = MAX_N * BK * 2 / CG;     // 24 KB, or 12 KB per CTA of a pair
+};
 constexpr int MAX_KB = 7;                        // K' <= 448 (K <= 149)
 constexpr int THREADS = 256;
 
@@ -50,23 +56,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {   // barrier given by its shared address
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// multicast variant: one L2 read lands in the same shared-memory offset of every CTA of the cluster in cta_mask, and
-// performs complete_tx on the mbarrier at the same offset in each of them
-__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -77,11 +82,59 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+// Pair kernel: barriers that are signalled from the other SM (remote arrive, multicast commit) are polled with test_wait
+// (measured: try_wait's suspended wait adds microseconds per hand-off when the completing arrival comes from a peer CTA)
+// same, without the cluster-scope release: for forwarding a completion the thread itself wrote nothing for
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// exactly one lane of the (converged) warp gets true.  The single-thread instructions (bulk copies, tcgen05.mma / commit)
+// are issued under this predicate from warp-uniform loops: under `if (lane == 0)` the compiler wraps every one of them in
+// an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~95 clocks per tcgen05.mma, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+template <int CG>
+__device__ __forceinline__ void mbar_wait_cg(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  else   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
 // LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
@@ -90,13 +143,45 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  else   // M = 256: rows 0-127 from the leader CTA's A image / TMEM, rows 128-255 from its peer; each CTA holds N/2 rows of B
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// descriptor passed as its low word (address field + LBO) - the high word is the constant (SBO 1024 B, version 1,
+// SWIZZLE_128B): the issuing loop then only adds small offsets to one 32-bit value per operand
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+template <int CG>
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -149,7 +234,13 @@ struct FusedParams {
   const float* vec; const float* ew; int lmax;
   float* sum; int d_out; float* cnt;
   long long n_edges;
+  int dbg_noload;                                    // diagnostics: skip the B copies (timing only, results garbage)
+  unsigned long long* dbg;                           // optional [16] clock counters (DDB200_FUSED_DEBUG=1), else nullptr
 };
+
+// clock counters of the warp roles: compiled in only for the DBG instantiation (DDB200_FUSED_DEBUG=1)
+#define DBG_T() (DBG ? clock64() : 0ll)
+#define DBG_ADD(i, v) do { if (DBG) atomicAdd(p.dbg + (i), (unsigned long long)(v)); } while (0)
 
 constexpr int MAX_TILES = 160, MAX_MENT = 256, MAX_TERMS = 512;
 
@@ -157,7 +248,7 @@ constexpr int MAX_TILES = 160, MAX_MENT = 256, MAX_TERMS = 512;
 template <int MULOUT, int DOUT, int ROWS>
 __device__ __forceinline__ void consume_tile(uint32_t taddr, const float* __restrict__ z, float* __restrict__ acc) {
   constexpr int NCOL = MULOUT * ROWS;
-  static_assert(NCOL % 32 == 0 && NCOL <= 256, "tile width");
+  static_assert(NCOL % 32 == 0 && NCOL <= MAX_N, "tile width");
 #pragma unroll
   for (int c = 0; c < NCOL / 32; ++c) {
     uint32_t v[32];
@@ -193,64 +284,79 @@ __device__ __forceinline__ void make_z(const float* __restrict__ xr, int nrow, c
 
 // z (global loads of the gathered node row + tiny matrix products) is formed BEFORE waiting for the accumulator, so that
 // its latency overlaps the tile's MMAs
-template <int MULOUT, int DOUT, int ROWS>
+template <int CG, int MULOUT, int DOUT, int ROWS>
 __device__ __forceinline__ void tile_body(uint32_t taddr, const float* xr, int nrow, int d_in, const float* M, float* acc,
                                           uint64_t* tfull_bar, uint32_t parity) {
   float z[ROWS * DOUT];
   if (d_in == 1) make_z<1, DOUT, ROWS>(xr, nrow, M, z);
   else make_z<3, DOUT, ROWS>(xr, nrow, M, z);
-  mbar_wait(tfull_bar, parity);
+  mbar_wait_cg<CG>(tfull_bar, parity);
   tc_fence_after();
   consume_tile<MULOUT, DOUT, ROWS>(taddr, z, acc);
 }
 
+template <int CG, bool DBG>
 __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParams p) {
+  constexpr int STAGES = Ring<CG>::STAGES, B_STAGE_BYTES = Ring<CG>::STAGE_BYTES;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int n_kb_max = p.n_kb > p.n_kb1 ? p.n_kb : p.n_kb1;
   unsigned char* sA = smem;                                      // n_kb_max x 16 KB
-  unsigned char* sB = smem + (size_t)n_kb_max * A_KB_BYTES;      // 3 x 32 KB ring
+  unsigned char* sB = smem + (size_t)n_kb_max * A_KB_BYTES;      // ring of B stages
   float* sY = reinterpret_cast<float*>(sB + STAGES * B_STAGE_BYTES);   // [9][128] spherical harmonics per consumer thread
   int* sTiles = reinterpret_cast<int*>(sY + 9 * 128);            // [MAX_TILES][8]
   int* sMent = sTiles + MAX_TILES * 8;                           // [MAX_MENT][2]
   int* sTermY = sMent + MAX_MENT * 2;                            // [MAX_TERMS]
   float* sTermV = reinterpret_cast<float*>(sTermY + MAX_TERMS);  // [MAX_TERMS]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sTermV + MAX_TERMS);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* a_ready = tempty + 2;
+  uint64_t* full = bars;                 // this CTA's part of B stage s has landed (TMA complete_tx)
+  uint64_t* empty = bars + STAGES;       // the MMAs reading stage s are done (commit; both CTAs of a pair)
+  uint64_t* pfull = bars + 2 * STAGES;   // leader only: the peer's part of stage s has landed (relayed by the peer)
+  uint64_t* tfull = bars + 3 * STAGES;
+  uint64_t* tempty = tfull + 2;          // leader: consumers of all CG CTAs have drained the accumulator
+  uint64_t* a_ready = tempty + 2;        // leader: all CG operand images hold A'
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   for (int i = tid; i < p.n_tiles * 8; i += THREADS) sTiles[i] = p.tiles[i];
   for (int i = tid; i < p.n_ment * 2; i += THREADS) sMent[i] = p.ment[i];
   for (int i = tid; i < p.n_terms; i += THREADS) { sTermY[i] = p.term_y[i]; sTermV[i] = p.term_v[i]; }
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
-    mbar_init(a_ready, 4);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&pfull[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * CG); }
+    mbar_init(a_ready, 4 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 2) {   // the same warp of both CTAs of a pair allocates (cute::TMEM::Allocator2Sm contract)
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);   // | (N >> 3) << 17 per tile
+  // instruction descriptor: f32 accumulate, bf16 x bf16, K-major both, M = 128 * CG; | (N >> 3) << 17 per tile
+  const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((BM * CG) >> 4) << 24);
   const int n1 = ((p.H + 15) / 16) * 16;
 
   const long long n_mtiles = (p.n_edges + BM - 1) / BM;
-  uint32_t pc = 0, mc = 0, ma = 0, ea = 0, mtc = 0;
+  const long long n_units = (n_mtiles + CG - 1) / CG;       // a unit = the CG edge tiles one MMA covers
+  uint32_t pc = 0, mc = 0, ma = 0, ea = 0, mtc = 0, rc = 0;
   const __nv_bfloat16 one = __float2bfloat16(1.0f), zero = __float2bfloat16(0.f);
 
-  for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-    __syncthreads();
+  for (long long unit = blockIdx.x / CG; unit < n_units; unit += gridDim.x / CG) {
+    const long long mt = unit * CG + rank;                   // may be one past the end for the peer: all rows invalid
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    const long long t_unit = DBG_T();
     // ---- A0' image: [hi | hi | lo | 1 1 | 0..] of [edge_attr | node[tgt,:ns] | node[src,:ns]] -----------------------
     {
       const long long e0 = mt * BM;
@@ -313,33 +419,71 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         put_a(sA, r, Kin + k, hi);
         put_a(sA, r, 2 * Kin + k, lo);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if constexpr (CG == 2) asm volatile("fence.proxy.async;" ::: "memory");
+      else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (tid == 0) DBG_ADD(10, DBG_T() - t_unit);
 
     if (warp == 0) {
       // ===== operand-B producer: W1' images, then one image set per N tile ====================================
-      if (lane == 0) {
+      // Only the rows the MMA reads (N of the tile) are fetched: images are row-major [256][128 B]; with a CTA pair this CTA
+      // fetches its half of them (rows [rank * N/2, (rank + 1) * N/2) feed the accumulator columns of the same range).
+      // The loop is kept lean (no divisions, 32-bit shared addresses, incremental source pointers): at ~400 clocks of MMA
+      // work per stage the producer's own instruction stream is otherwise what starves the tensor pipe.
+      {
+        const uint32_t sB0 = smem_u32(sB), full0 = smem_u32(full), empty0 = smem_u32(empty);
+        for (int t = -1; t < p.n_tiles; ++t) {
+          const int nkb = (t < 0) ? p.n_kb1 : p.n_kb;
+          const uint32_t bytes = (uint32_t)(((t < 0) ? n1 : sTiles[t * 8 + 1]) / CG) * 128u;
+          const unsigned char* src = ((t < 0) ? reinterpret_cast<const unsigned char*>(p.w1img)
+                                              : reinterpret_cast<const unsigned char*>(p.w2img) +
+                                                    (size_t)t * p.n_kb * B_IMAGE_BYTES) + (size_t)rank * bytes;
+          for (int kb = 0; kb < nkb; ++kb, ++pc, src += B_IMAGE_BYTES) {
+            const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
+            const long long t0 = DBG_T();
+            mbar_wait_u32(empty0 + s * 8, ph ^ 1);
+            if (lane == 0) DBG_ADD(5, DBG_T() - t0);
+            if (elect_one()) {
+              if (DBG && p.dbg_noload) mbar_arrive(&full[s]);
+              else {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + s * 8), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sB0 + s * B_STAGE_BYTES), "l"(src), "r"(bytes), "r"(full0 + s * 8) : "memory");
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else if (warp == 3 && CG == 2) {
+      // ===== relay (peer CTA only): tell the leader's MMA thread that this CTA's half of a stage has landed ===========
+      // (a plain bulk copy can only complete_tx on a barrier of the CTA it writes to - measured: signalling the leader's
+      // barrier directly hangs - so the peer forwards the completion with a remote arrive)
+      if (!leader) {
         const int total = p.n_kb1 + p.n_tiles * p.n_kb;
-        for (int i = 0; i < total; ++i, ++pc) {
-          const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          // only the rows the MMA reads (N of the tile) are fetched: images are row-major [256][128 B]
-          const int rows = (i < p.n_kb1) ? n1 : sTiles[((i - p.n_kb1) / p.n_kb) * 8 + 1];
-          const uint32_t bytes = (uint32_t)rows * 128u;
-          mbar_expect_tx(&full[s], bytes);
-          const unsigned char* src = (i < p.n_kb1)
-              ? reinterpret_cast<const unsigned char*>(p.w1img) + (size_t)i * B_STAGE_BYTES
-              : reinterpret_cast<const unsigned char*>(p.w2img) + (size_t)(i - p.n_kb1) * B_STAGE_BYTES;
-          bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, bytes, &full[s]);
+        for (int i = 0; i < total; ++i, ++rc) {
+          const uint32_t s = rc % STAGES, ph = (rc / STAGES) & 1;
+          const long long t0 = DBG_T();
+          mbar_wait(&full[s], ph);
+          const long long t1 = DBG_T();
+          if (elect_one()) mbar_arrive_remote_relaxed(&pfull[s], 0);
+          __syncwarp();
+          if (lane == 0) { DBG_ADD(6, t1 - t0); DBG_ADD(7, DBG_T() - t1); }
         }
       }
     } else if (warp == 1) {
-      // ===== MMA issuer ======================================================================================
-      if (lane == 0) {
+      // ===== MMA issuer (leader CTA of a pair only) ================================================================
+      if (leader) {
+        const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), b_lo0 = umma_desc_lo(smem_u32(sB));
+        const uint32_t full0 = smem_u32(full), pfull0 = smem_u32(pfull);
+        const long long t_role = DBG_T();
+        long long w_te = 0, w_full = 0, w_a = 0, b_issue = 0;
         for (int t = -1; t < p.n_tiles; ++t, ++ma) {
           const uint32_t buf = ma & 1, aph = (ma >> 1) & 1;
-          mbar_wait(&tempty[buf], aph ^ 1);
+          long long t0 = DBG_T();
+          mbar_wait_cg<CG>(&tempty[buf], aph ^ 1);
+          w_te += DBG_T() - t0;
           tc_fence_after();
           const uint32_t d = tmem_base + buf * BN;
           const int nkb = (t < 0) ? p.n_kb1 : p.n_kb;
@@ -347,19 +491,33 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
           const uint32_t idesc = idesc0 | ((uint32_t)(nmma >> 3) << 17);
           for (int kb = 0; kb < nkb; ++kb, ++mc) {
             const uint32_t s = mc % STAGES, ph = (mc / STAGES) & 1;
-            mbar_wait(&full[s], ph);
+            t0 = DBG_T();
+            mbar_wait_u32(full0 + s * 8, ph);
+            if constexpr (CG == 2) mbar_wait_u32(pfull0 + s * 8, ph);
+            w_full += DBG_T() - t0;
+            t0 = DBG_T();
             tc_fence_after();
-            const uint32_t a0 = smem_u32(sA + (size_t)kb * A_KB_BYTES), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+            const uint32_t a_lo = a_lo0 + kb * (A_KB_BYTES >> 4), b_lo = b_lo0 + s * (B_STAGE_BYTES >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)
-              umma_bf16(d, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kb | kk) != 0);
-            umma_commit(&empty[s]);
+              for (int kk = 0; kk < BK / 16; ++kk)
+                umma_bf16_lo<CG>(d, a_lo + kk * 2, b_lo + kk * 2, idesc, (kb | kk) != 0);
+              umma_commit<CG>(&empty[s]);
+              if (kb == nkb - 1) umma_commit<CG>(&tfull[buf]);
+            }
+            __syncwarp();
+            b_issue += DBG_T() - t0;
           }
-          umma_commit(&tfull[buf]);
-          if (t < 0) {          // hidden layer done: wait until the consumers have rewritten the operand image as A'
-            mbar_wait(a_ready, mtc & 1);
+          if (t < 0) {          // hidden layer done: wait until the consumers have rewritten the operand image(s) as A'
+            t0 = DBG_T();
+            if constexpr (CG == 2) mbar_wait_cluster(a_ready, mtc & 1); else mbar_wait(a_ready, mtc & 1);
+            w_a += DBG_T() - t0;
             tc_fence_after();
           }
+        }
+        if (lane == 0) {
+          DBG_ADD(0, DBG_T() - t_role); DBG_ADD(1, w_te); DBG_ADD(2, w_full); DBG_ADD(3, w_a);
+          DBG_ADD(13, b_issue); DBG_ADD(14, (long long)(p.n_kb1 + p.n_tiles * p.n_kb) * 4);
         }
       }
     } else if (warp >= 4) {
@@ -386,7 +544,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
       const float* xrow = p.x + (long long)src_e * p.ld_x;
       {   // hidden activations: ReLU (bias already folded), bf16 split, written back over the operand image as A'
         const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
-        mbar_wait(&tfull[buf], aph);
+        const long long t0 = DBG_T();
+        mbar_wait_cg<CG>(&tfull[buf], aph);
+        if (tid == 128) DBG_ADD(9, DBG_T() - t0);
         tc_fence_after();
         const int K = p.H, kpad = p.n_kb * BK;
         for (int c0 = 0; c0 < K; c0 += 32) {
@@ -423,13 +583,18 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
           }
         }
         for (int col = 3 * K; col < kpad; ++col) put_a(sA, ct, col, col < 3 * K + 2 ? one : zero);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if constexpr (CG == 2) asm volatile("fence.proxy.async;" ::: "memory");
+        else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&tempty[buf]); mbar_arrive(a_ready); }
+        if (lane == 0) {
+          if constexpr (CG == 2) { mbar_arrive_remote_relaxed(&tempty[buf], 0); mbar_arrive_remote(a_ready, 0); }
+          else { mbar_arrive(&tempty[buf]); mbar_arrive(a_ready); }
+        }
         ++ea;
       }
       float acc[48];
+      const long long t_loop = DBG_T();
       for (int t = 0; t < p.n_tiles; ++t, ++ea) {
         const int* ti = sTiles + t * 8;
         const int kind = ti[0], x_off = ti[2], nrow = ti[3], d_in = ti[4], out_off = ti[5], flags = ti[6];
@@ -458,14 +623,16 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         const float* xr = xrow + x_off;
         switch (kind) {
-          case 0: tile_body<48, 1, 4>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
-          case 1: tile_body<10, 3, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
-          case 2: tile_body<16, 1, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
-          default: tile_body<4, 3, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
+          case 0: tile_body<CG, 48, 1, 4>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
+          case 1: tile_body<CG, 10, 3, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
+          case 2: tile_body<CG, 16, 1, 8>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
+          default: tile_body<CG, 4, 3, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_remote_relaxed(&tempty[buf], 0); else mbar_arrive(&tempty[buf]);
+        }
         if (flags & 2) {   // end of an output irrep: scatter-add (pre-reduced over the warp when all lanes share the target)
           const int nacc = (kind == 0) ? 48 : (kind == 1 ? 30 : (kind == 2 ? 16 : 12));
           const int d0 = __shfl_sync(0xffffffffu, dst_e, 0);
@@ -488,18 +655,46 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
           }
         }
       }
+      if (tid == 128) DBG_ADD(8, DBG_T() - t_loop);
       if (p.cnt && valid) atomicAdd(p.cnt + dst_e, 1.f);
     }
+    if (tid == 0) { DBG_ADD(11, DBG_T() - t_unit); DBG_ADD(12, 1); }
     ++mtc;
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
 }  // namespace
+
+static unsigned long long* fused_debug_buffer() {
+  static unsigned long long* buf = [] {
+    const char* e = getenv("DDB200_FUSED_DEBUG");
+    unsigned long long* b = nullptr;
+    if (e && atoi(e) != 0 && cudaMalloc(&b, 16 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(b, 0, 16 * sizeof(unsigned long long));
+    return b;
+  }();
+  return buf;
+}
+
+// Diagnostics (DDB200_FUSED_DEBUG=1 only): copies the 16 clock counters of the fused kernel's warp roles to `out` and
+// clears them.  [0] MMA role total, [1] wait accumulator-free, [2] wait B stage, [3] wait A', [5] producer wait stage-free,
+// [8] consumer tile loop, [9] consumer wait hidden, [10] A0 build, [11] unit total, [12] units.  Synchronises the device.
+extern "C" int ddb200_fused_debug_read(uint64_t* out) {
+  unsigned long long* b = fused_debug_buffer();
+  if (!b || !out) return DDB200_EINVAL;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, b, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(b, 0, 16 * sizeof(unsigned long long));
+  return (int)e;
+}
 
 extern "C" int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, const float* node, int64_t ld_node, int ns,
                                  const int32_t* tgt, const int32_t* src, const void* w1_images, int hidden,
@@ -514,7 +709,7 @@ extern "C" int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, 
   if (n_tiles > MAX_TILES || n_ment > MAX_MENT || n_terms > MAX_TERMS || sh_lmax < 0 || sh_lmax > 2) return DDB200_EINVAL;
   const int K1 = ne + 2 * ns;
   const int n_kb = (3 * hidden + 2 + BK - 1) / BK, n_kb1 = (3 * K1 + 2 + BK - 1) / BK;
-  if (n_kb > MAX_KB || n_kb1 > MAX_KB || hidden > BN) return DDB200_EINVAL;
+  if (n_kb > MAX_KB || n_kb1 > MAX_KB || hidden > MAX_N) return DDB200_EINVAL;
   if ((reinterpret_cast<uintptr_t>(w1_images) & 127) || (reinterpret_cast<uintptr_t>(w2_images) & 127)) return DDB200_EINVAL;
   if (n_edges == 0) return 0;
   FusedParams p = {};
@@ -524,21 +719,51 @@ extern "C" int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, 
   p.ment = ment; p.term_y = term_y; p.term_v = term_v; p.n_ment = n_ment; p.n_terms = n_terms;
   p.x = x; p.ld_x = ld_x; p.vec = edge_vec; p.ew = edge_weight; p.lmax = sh_lmax; p.sum = sum; p.d_out = d_out; p.cnt = cnt;
   p.n_edges = n_edges;
+  p.dbg = fused_debug_buffer();
+  static const int noload = [] { const char* e = getenv("DDB200_FUSED_NOLOAD"); return e ? atoi(e) : 0; }();
+  p.dbg_noload = p.dbg ? noload : 0;
   const int n_kb_max = n_kb > n_kb1 ? n_kb : n_kb1;
-  const size_t smem = (size_t)n_kb_max * A_KB_BYTES + STAGES * B_STAGE_BYTES + 9 * 128 * 4 + MAX_TILES * 8 * 4 +
-                      MAX_MENT * 2 * 4 + MAX_TERMS * 8 + 16 * sizeof(uint64_t) + 1024;
-  if (smem > 227 * 1024) return DDB200_ESMEM;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(fused_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_mtiles = (n_edges + BM - 1) / BM;
-  const unsigned grid = (unsigned)(n_mtiles < sms ? n_mtiles : sms);
-  fused_conv_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
-  return (int)cudaGetLastError();
+  // CTA pairs (tcgen05 cta_group::2) unless disabled; every tile width of the plan (192/160/256/64, hidden rounded to 16)
+  // splits into two halves of whole 8-row swizzle atoms
+  static const int pair_env = [] { const char* e = getenv("DDB200_FUSED_CTA_PAIR"); return e ? atoi(e) : 1; }();
+  const bool pair = pair_env != 0 && n_mtiles >= 2;
+  const size_t fixed = 9 * 128 * 4 + MAX_TILES * 8 * 4 + MAX_MENT * 2 * 4 + MAX_TERMS * 8 + 32 * sizeof(uint64_t) + 1024;
+  const size_t smem = (size_t)n_kb_max * A_KB_BYTES + fixed +
+                      (pair ? Ring<2>::STAGES * Ring<2>::STAGE_BYTES : Ring<1>::STAGES * Ring<1>::STAGE_BYTES);
+  if (smem > 227 * 1024) return DDB200_ESMEM;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaSuccess;
+    const void* fns[4] = {(const void*)fused_conv_kernel<1, false>, (const void*)fused_conv_kernel<2, false>,
+                          (const void*)fused_conv_kernel<1, true>, (const void*)fused_conv_kernel<2, true>};
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  if (!pair) {
+    const unsigned grid = (unsigned)(n_mtiles < sms ? n_mtiles : sms);
+    if (p.dbg) fused_conv_kernel<1, true><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+    else fused_conv_kernel<1, false><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+  }
+  const long long n_units = (n_mtiles + 1) / 2;
+  const long long max_pairs = sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (n_units < max_pairs ? n_units : max_pairs)));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = p.dbg ? cudaLaunchKernelEx(&cfg, fused_conv_kernel<2, true>, p)
+                        : cudaLaunchKernelEx(&cfg, fused_conv_kernel<2, false>, p);
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }

@@ -6,7 +6,7 @@ tensor (11-28 KB per edge) never exists in HBM.  To make that possible the weigh
 whole rows ``u`` of one path block ``[mul_in, mul_out]``:
 
     (mul_out, 2l_out+1) = (48, 1): 4 rows x 48 columns = 192        (10, 3): 16 rows x 10 columns = 160
-    (16, 1): 16 x 16 = 256                                           (4, 3): 16 x 4 = 64
+    (16, 1): 8 x 16 = 128                                            (4, 3): 16 x 4 = 64
 
 so that a consumer thread (one edge = one TMEM lane) knows at compile time which register of its accumulator every
 TMEM column feeds.  This module builds, from a ``TpTable`` and the radial MLP's second Linear:
@@ -30,7 +30,7 @@ from .radial import BK, BN
 from .tp_table import TpTable
 
 # (mul_out, d_out) -> (consumer kind id, rows per tile)
-CONSUMER_KINDS = {(48, 1): (0, 4), (10, 3): (1, 16), (16, 1): (2, 16), (4, 3): (3, 16)}
+CONSUMER_KINDS = {(48, 1): (0, 4), (10, 3): (1, 16), (16, 1): (2, 8), (4, 3): (3, 16)}
 MAX_K = 144
 ENABLED = os.environ.get('DDB200_FUSED_CONV', '1') != '0'
 

@@ -157,6 +157,12 @@ int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, const float
                       const float* term_v, int n_terms, const float* x, int64_t ld_x, const float* edge_vec,
                       const float* edge_weight, int sh_lmax, int64_t n_edges, float* sum, int d_out, float* cnt,
                       void* stream);
+/* Execution: CTA pairs on tcgen05 cta_group::2 (256 edges per MMA, each CTA stages half of every weight image);
+ * DDB200_FUSED_CTA_PAIR=0 selects the single-CTA kernel. */
+
+/* Diagnostics, no reference counterpart: with DDB200_FUSED_DEBUG=1 in the environment the fused kernel accumulates clock
+ * counters per warp role; this copies the 16 counters to `out` (host) and clears them.  DDB200_EINVAL when disabled. */
+int ddb200_fused_debug_read(uint64_t* out);
 
 #ifdef __cplusplus
 }
