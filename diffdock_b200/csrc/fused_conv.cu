@@ -263,36 +263,49 @@ __device__ __forceinline__ void consume_tile(uint32_t taddr, const float* __rest
   }
 }
 
-// z[r, k] = sum_i x[x_off + r*DIN + i] * M[i, k] for the tile's rows (0 beyond the valid ones)
+// z[r, k] = sum_i x[x_off + r*DIN + i] * M[i, k] for the tile's rows; xv = the tile's gathered node values (prefetched into
+// registers one tile ahead, zero beyond the valid rows)
 template <int DIN, int DOUT, int ROWS>
-__device__ __forceinline__ void make_z(const float* __restrict__ xr, int nrow, const float* __restrict__ M,
-                                       float* __restrict__ z) {
+__device__ __forceinline__ void make_z(const float* __restrict__ xv, const float* __restrict__ M, float* __restrict__ z) {
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
-    float xv[DIN];
-#pragma unroll
-    for (int i = 0; i < DIN; ++i) xv[i] = (r < nrow) ? __ldg(xr + r * DIN + i) : 0.f;
 #pragma unroll
     for (int k = 0; k < DOUT; ++k) {
       float a = 0.f;
 #pragma unroll
-      for (int i = 0; i < DIN; ++i) a = fmaf(xv[i], M[i * 3 + k], a);
+      for (int i = 0; i < DIN; ++i) a = fmaf(xv[r * DIN + i], M[i * 3 + k], a);
       z[r * DOUT + k] = a;
     }
   }
 }
 
-// z (global loads of the gathered node row + tiny matrix products) is formed BEFORE waiting for the accumulator, so that
-// its latency overlaps the tile's MMAs
+constexpr int XN = 48;     // gathered node values of one tile: at most 16 rows x 3 components
+__device__ __forceinline__ void prefetch_x(const float* __restrict__ src, int cnt, float* __restrict__ xn) {
+#pragma unroll
+  for (int j = 0; j < XN; ++j) xn[j] = (j < cnt) ? __ldg(src + j) : 0.f;
+}
+
+// z is formed from the node values prefetched during the previous tile, then the NEXT tile's values are requested, all
+// before waiting for the accumulator: the gather latency overlaps this tile's contraction
 template <int CG, int MULOUT, int DOUT, int ROWS>
-__device__ __forceinline__ void tile_body(uint32_t taddr, const float* xr, int nrow, int d_in, const float* M, float* acc,
-                                          uint64_t* tfull_bar, uint32_t parity) {
+__device__ __forceinline__ void tile_body(uint32_t taddr, float* xn, int d_in, const float* M, float* acc,
+                                          const float* xnext, int cnt_next, uint64_t* tfull_bar, uint32_t parity,
+                                          unsigned long long* dbg) {
   float z[ROWS * DOUT];
-  if (d_in == 1) make_z<1, DOUT, ROWS>(xr, nrow, M, z);
-  else make_z<3, DOUT, ROWS>(xr, nrow, M, z);
+  const long long t0 = dbg ? clock64() : 0ll;
+  if (d_in == 1) make_z<1, DOUT, ROWS>(xn, M, z);
+  else make_z<3, DOUT, ROWS>(xn, M, z);
+  prefetch_x(xnext, cnt_next, xn);
+  const long long t1 = dbg ? clock64() : 0ll;
   mbar_wait_cg<CG>(tfull_bar, parity);
   tc_fence_after();
+  const long long t2 = dbg ? clock64() : 0ll;
   consume_tile<MULOUT, DOUT, ROWS>(taddr, z, acc);
+  if (dbg) {
+    atomicAdd(dbg + 22, (unsigned long long)(t1 - t0));
+    atomicAdd(dbg + 23, (unsigned long long)(t2 - t1));
+    atomicAdd(dbg + 24, (unsigned long long)(clock64() - t2));
+  }
 }
 
 template <int CG, bool DBG>
@@ -527,6 +540,17 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
       const bool valid = e < p.n_edges;
       const int src_e = valid ? __ldg(p.src + e) : 0, dst_e = valid ? __ldg(p.tgt + e) : -1;
       const float ew_e = (valid && p.ew) ? __ldg(p.ew + e) : 1.f;
+      // runs of equal scatter targets inside the warp (rows past the end sort last)
+      const int seg_key = valid ? dst_e : 0x7fffffff;
+      const int key_dn = __shfl_down_sync(0xffffffffu, seg_key, 1), key_up = __shfl_up_sync(0xffffffffu, seg_key, 1);
+      const bool seg_sorted = __all_sync(0xffffffffu, lane == 31 || key_dn >= seg_key);
+      const bool seg_head = lane == 0 || key_up != seg_key;
+      uint32_t seg_same = 0;      // bit o: lane + 2^o belongs to the same run
+#pragma unroll
+      for (int o = 0; o < 5; ++o) {
+        const int ko = __shfl_down_sync(0xffffffffu, seg_key, 1u << o);
+        if (lane + (1 << o) < 32 && ko == seg_key) seg_same |= 1u << o;
+      }
       {   // real spherical harmonics of the edge vector, component normalisation (e3nn polynomials)
         float vx = valid ? __ldg(p.vec + 3 * e) : 1.f, vy = valid ? __ldg(p.vec + 3 * e + 1) : 0.f,
               vz = valid ? __ldg(p.vec + 3 * e + 2) : 0.f;
@@ -593,18 +617,23 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         }
         ++ea;
       }
-      float acc[48];
+      float acc[48], xn[XN], M[9];
       const long long t_loop = DBG_T();
+      prefetch_x(xrow + sTiles[2], sTiles[3] * sTiles[4], xn);
       for (int t = 0; t < p.n_tiles; ++t, ++ea) {
         const int* ti = sTiles + t * 8;
-        const int kind = ti[0], x_off = ti[2], nrow = ti[3], d_in = ti[4], out_off = ti[5], flags = ti[6];
+        const int kind = ti[0], d_in = ti[4], out_off = ti[5], flags = ti[6];
+        const int tn = (t + 1 < p.n_tiles) ? t + 1 : t;          // next tile (the last one re-requests its own rows)
+        const float* xnext = xrow + sTiles[tn * 8 + 2];
+        const int cnt_next = (t + 1 < p.n_tiles) ? sTiles[tn * 8 + 3] * sTiles[tn * 8 + 4] : 0;
         if (flags & 1) {
 #pragma unroll
           for (int i = 0; i < 48; ++i) acc[i] = 0.f;
         }
-        // M[i,k] = edge_weight * sum_j coef*C[i,j,k] * Y[j]  (at most 3x3 for the supported paths; row-major, stride 3)
-        float M[9];
-        {
+        // M[i,k] = edge_weight * sum_j coef*C[i,j,k] * Y[j]  (at most 3x3 for the supported paths; row-major, stride 3),
+        // rebuilt only when the tile belongs to another path than its predecessor
+        const long long tm0 = DBG_T();
+        if (flags & 4) {
           const int dout = (kind == 0 || kind == 2) ? 1 : 3;
           const int* me = sMent + ti[7] * 2;
 #pragma unroll
@@ -621,30 +650,39 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         }
         const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-        const float* xr = xrow + x_off;
+        const long long tm1 = DBG_T();
         switch (kind) {
-          case 0: tile_body<CG, 48, 1, 4>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
-          case 1: tile_body<CG, 10, 3, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
-          case 2: tile_body<CG, 16, 1, 8>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
-          default: tile_body<CG, 4, 3, 16>(taddr, xr, nrow, d_in, M, acc, &tfull[buf], aph); break;
+          case 0: tile_body<CG, 48, 1, 4>(taddr, xn, d_in, M, acc, xnext, cnt_next, &tfull[buf], aph, (DBG && tid == 128) ? p.dbg : nullptr); break;
+          case 1: tile_body<CG, 10, 3, 16>(taddr, xn, d_in, M, acc, xnext, cnt_next, &tfull[buf], aph, (DBG && tid == 128) ? p.dbg : nullptr); break;
+          case 2: tile_body<CG, 16, 1, 8>(taddr, xn, d_in, M, acc, xnext, cnt_next, &tfull[buf], aph, (DBG && tid == 128) ? p.dbg : nullptr); break;
+          default: tile_body<CG, 4, 3, 16>(taddr, xn, d_in, M, acc, xnext, cnt_next, &tfull[buf], aph, (DBG && tid == 128) ? p.dbg : nullptr); break;
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if constexpr (CG == 2) mbar_arrive_remote_relaxed(&tempty[buf], 0); else mbar_arrive(&tempty[buf]);
         }
-        if (flags & 2) {   // end of an output irrep: scatter-add (pre-reduced over the warp when all lanes share the target)
+        const long long tm2 = DBG_T();
+        if (DBG && tid == 128) {
+          DBG_ADD(16, tm1 - tm0);
+          if (kind == 0) DBG_ADD(17, tm2 - tm1); else DBG_ADD(18, tm2 - tm1);
+          if (kind == 0) DBG_ADD(19, 1); else DBG_ADD(20, 1);
+        }
+        if (flags & 2) {   // end of an output irrep: scatter-add, pre-reduced over runs of equal targets within the warp
           const int nacc = (kind == 0) ? 48 : (kind == 1 ? 30 : (kind == 2 ? 16 : 12));
-          const int d0 = __shfl_sync(0xffffffffu, dst_e, 0);
-          const bool uniform = __all_sync(0xffffffffu, dst_e == d0) && d0 >= 0;
-          if (uniform) {
+          if (seg_sorted) {
+            // CSR order: equal targets are contiguous lanes -> segmented shuffle reduction, one atomic per run and value
+            // (the edges of a 24-neighbour receptor node span at most two warps: ~2-3 atomics instead of 32)
 #pragma unroll
             for (int i = 0; i < 48; ++i) {
               if (i < nacc) {
                 float v = acc[i];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == (i & 31)) atomicAdd(p.sum + (long long)d0 * p.d_out + out_off + i, v);
+                for (int o = 0; o < 5; ++o) {
+                  const float tv = __shfl_down_sync(0xffffffffu, v, 1u << o);
+                  if ((seg_same >> o) & 1) v += tv;
+                }
+                if (seg_head && valid) atomicAdd(p.sum + (long long)dst_e * p.d_out + out_off + i, v);
               }
             }
           } else if (valid) {
@@ -653,10 +691,21 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
             for (int i = 0; i < 48; ++i)
               if (i < nacc) atomicAdd(srow + i, acc[i]);
           }
+          if (DBG && tid == 128) DBG_ADD(21, DBG_T() - tm2);
         }
       }
       if (tid == 128) DBG_ADD(8, DBG_T() - t_loop);
-      if (p.cnt && valid) atomicAdd(p.cnt + dst_e, 1.f);
+      if (p.cnt) {
+        if (seg_sorted) {
+          float v = 1.f;
+#pragma unroll
+          for (int o = 0; o < 5; ++o) {
+            const float tv = __shfl_down_sync(0xffffffffu, v, 1u << o);
+            if ((seg_same >> o) & 1) v += tv;
+          }
+          if (seg_head && valid) atomicAdd(p.cnt + dst_e, v);
+        } else if (valid) atomicAdd(p.cnt + dst_e, 1.f);
+      }
     }
     if (tid == 0) { DBG_ADD(11, DBG_T() - t_unit); DBG_ADD(12, 1); }
     ++mtc;
@@ -677,22 +726,22 @@ static unsigned long long* fused_debug_buffer() {
   static unsigned long long* buf = [] {
     const char* e = getenv("DDB200_FUSED_DEBUG");
     unsigned long long* b = nullptr;
-    if (e && atoi(e) != 0 && cudaMalloc(&b, 16 * sizeof(unsigned long long)) == cudaSuccess)
-      cudaMemset(b, 0, 16 * sizeof(unsigned long long));
+    if (e && atoi(e) != 0 && cudaMalloc(&b, 32 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(b, 0, 32 * sizeof(unsigned long long));
     return b;
   }();
   return buf;
 }
 
-// Diagnostics (DDB200_FUSED_DEBUG=1 only): copies the 16 clock counters of the fused kernel's warp roles to `out` and
+// Diagnostics (DDB200_FUSED_DEBUG=1 only): copies the 32 clock counters of the fused kernel's warp roles to `out` and
 // clears them.  [0] MMA role total, [1] wait accumulator-free, [2] wait B stage, [3] wait A', [5] producer wait stage-free,
 // [8] consumer tile loop, [9] consumer wait hidden, [10] A0 build, [11] unit total, [12] units.  Synchronises the device.
 extern "C" int ddb200_fused_debug_read(uint64_t* out) {
   unsigned long long* b = fused_debug_buffer();
   if (!b || !out) return DDB200_EINVAL;
   cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(out, b, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess) e = cudaMemset(b, 0, 16 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemcpy(out, b, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(b, 0, 32 * sizeof(unsigned long long));
   return (int)e;
 }
 

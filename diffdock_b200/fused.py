@@ -93,6 +93,7 @@ class FusedPlan:
                         term_y.append(p.sh_off + j)
                         term_v.append(p.coef * C[i, j, k])
         group_prev = None
+        path_prev = None
         for p in paths:
             d_in, d_out = 2 * p.l_in + 1, 2 * p.l_out + 1
             kind, rows_per = CONSUMER_KINDS[(p.mul_out, d_out)]
@@ -101,7 +102,10 @@ class FusedPlan:
                 n_mma = rows_per * p.mul_out      # always the full tile: no stale TMEM columns are ever read
                 first = group_prev != p.i_out
                 group_prev = p.i_out
-                tiles.append([kind, n_mma, p.in_off + u0 * d_in, nrow, d_in, p.out_off, 1 if first else 0, mt_off[id(p)]])
+                new_path = path_prev is not p        # flag 4: the consumer rebuilds its C.Y matrix
+                path_prev = p
+                tiles.append([kind, n_mma, p.in_off + u0 * d_in, nrow, d_in, p.out_off,
+                              (1 if first else 0) | (4 if new_path else 0), mt_off[id(p)]])
                 src = np.full(BN, -1, dtype=np.int64)
                 cols = p.w_ref_off + (u0 * p.mul_out) + np.arange(nrow * p.mul_out)
                 src[:nrow * p.mul_out] = cols

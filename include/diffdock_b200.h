@@ -161,7 +161,7 @@ int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, const float
  * DDB200_FUSED_CTA_PAIR=0 selects the single-CTA kernel. */
 
 /* Diagnostics, no reference counterpart: with DDB200_FUSED_DEBUG=1 in the environment the fused kernel accumulates clock
- * counters per warp role; this copies the 16 counters to `out` (host) and clears them.  DDB200_EINVAL when disabled. */
+ * counters per warp role; this copies the 32 counters to `out` (host, uint64_t[32]) and clears them.  DDB200_EINVAL when disabled. */
 int ddb200_fused_debug_read(uint64_t* out);
 
 #ifdef __cplusplus

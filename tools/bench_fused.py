@@ -13,7 +13,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 NAMES = {0: 'mma_role', 1: 'mma_wait_acc_free', 2: 'mma_wait_B', 3: 'mma_wait_A2', 5: 'prod_wait_stage_free', 6: 'relay_wait_full', 7: 'relay_arrive',
-         8: 'cons_tile_loop', 9: 'cons_wait_hidden', 10: 'a0_build', 11: 'unit_total', 12: 'units'}
+         8: 'cons_tile_loop', 9: 'cons_wait_hidden', 10: 'a0_build', 16: 'cons_M_build', 17: 'cons_body_kind0', 18: 'cons_body_other', 19: 'n_kind0', 20: 'n_other',
+         21: 'cons_flush', 22: 'cons_z', 23: 'cons_wait_acc', 24: 'cons_fma', 11: 'unit_total', 12: 'units'}
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
@@ -47,7 +48,7 @@ if __name__ == '__main__':
     for _ in range(2):
         run()
     torch.cuda.synchronize()
-    dbg = (C.c_uint64 * 16)()
+    dbg = (C.c_uint64 * 32)()
     have_dbg = _lib.lib().ddb200_fused_debug_read(dbg) == 0
     ts = []
     for _ in range(5):
