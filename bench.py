@@ -165,7 +165,7 @@ def workload_config(cli, poses):
             "poses_per_gpu": poses, "n_res": cli.n_res, "n_atoms": cli.n_atoms, "sh_lmax": cli.sh_lmax,
             "l2": "per-step working set (edge embeddings ~0.3 GB per receptor edge group and layer, operand images, "
                   "node tensors) exceeds the 126 MB L2; no explicit flush",
-            "warmup_executed": max(cli.warmup, N_SCHED),
+            "warmup_executed": cli.warmup if getattr(cli, 'short_warmup', False) else max(cli.warmup, N_SCHED),
             "parallelism": f"poses sharded over {cli.gpus} GPU(s), no data-path collective"}
 
 
@@ -265,7 +265,7 @@ def run_cuda(cli):
     # Warm-up: the W requested steps, extended to one full pass over the 20-point schedule: every step of the schedule
     # has its own neighbour-list sizes, and the first visit of each grows torch's caching allocator (cudaMalloc + sync).
     # Measured: 67.0 ms/step when only steps 0-2 were warmed, 57.4 ms/step on the second pass over the same steps.
-    n_warm = max(cli.warmup, N_SCHED)
+    n_warm = cli.warmup if cli.short_warmup else max(cli.warmup, N_SCHED)
     for i in range(n_warm):
         step(i + cli.warmup - n_warm)
     sync_all()
@@ -336,7 +336,11 @@ def run_cuda(cli):
             peak_tf = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
             roof = {"bound": "tensor", "kernel": "fused_conv_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": ach / peak_tf, "peak_kind": pk_kind + " (sustained bf16 cuBLAS: kernel timed inside a long step)",
-                    "traffic": None, "launches": prof['fused_launches'],
+                    "traffic": None,
+                    "traffic_ncu": {"dram_bytes_per_launch": 151.7e6, "edges_per_launch": 400000,
+                                    "source": "profiles/r01i_fused_summary.csv (tools/bench_fused.py under ncu --set full); "
+                                              "the un-fused formulation moves 11.4 GB for the same launch"},
+                    "launches": prof['fused_launches'],
                     "timing": "CUDA-event pair per launch on the launching stream, over a replay of the timed K steps "
                               "(the timed region itself carries no per-launch events)",
                     "replay_ms_per_step": prof['replay_ms_per_step'],
@@ -388,6 +392,8 @@ def main():
     ap.add_argument('--sh-lmax', dest='sh_lmax', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
+    ap.add_argument('--short-warmup', dest='short_warmup', action='store_true',
+                    help='warm up exactly --warmup steps instead of a full schedule pass (runs under ncu)')
     cli = ap.parse_args()
     cli.warmup = max(cli.warmup, 0)
     if cli.impl == 'reference':
