@@ -47,3 +47,39 @@ class AtomEncoder(nn.Module):
         if self.additional_features_dim > 0:
             h = self.additional_features_embedder(torch.cat([h, x[:, nc:].to(h.dtype)], dim=1))
         return h
+
+
+class OldAtomEncoder(nn.Module):
+    """models/layers.py:70-117: categorical embeddings + Linear(scalar features incl. sigma embedding), then an optional
+    Linear([emb | LM columns]) - the encoder of the confidence model.  ``lm_embedding_dim`` (1280 in the reference,
+    hard-wired for 'esm') is a keyword here so that small fixtures can be loaded."""
+
+    def __init__(self, emb_dim, feature_dims, sigma_embed_dim, lm_embedding_type=None, lm_embedding_dim=1280):
+        super().__init__()
+        self.atom_embedding_list = nn.ModuleList()
+        self.num_categorical_features = len(feature_dims[0])
+        self.num_scalar_features = feature_dims[1] + sigma_embed_dim
+        self.lm_embedding_type = lm_embedding_type
+        for dim in feature_dims[0]:
+            emb = nn.Embedding(dim, emb_dim)
+            nn.init.xavier_uniform_(emb.weight.data)
+            self.atom_embedding_list.append(emb)
+        if self.num_scalar_features > 0:
+            self.linear = nn.Linear(self.num_scalar_features, emb_dim)
+        if lm_embedding_type is not None:
+            if lm_embedding_type != 'esm':
+                raise ValueError('LM Embedding type was not correctly determined. LM embedding type: ', lm_embedding_type)
+            self.lm_embedding_dim = lm_embedding_dim
+            self.lm_embedding_layer = nn.Linear(self.lm_embedding_dim + emb_dim, emb_dim)
+
+    def forward(self, x):
+        nc, nsf = self.num_categorical_features, self.num_scalar_features
+        assert x.shape[1] == nc + nsf + (self.lm_embedding_dim if self.lm_embedding_type is not None else 0)
+        out = 0
+        for i in range(nc):
+            out = out + self.atom_embedding_list[i](x[:, i].long())
+        if nsf > 0:
+            out = out + self.linear(x[:, nc:nc + nsf].float())
+        if self.lm_embedding_type is not None:
+            out = self.lm_embedding_layer(torch.cat([out, x[:, -self.lm_embedding_dim:].float()], 1))
+        return out

@@ -325,7 +325,31 @@ class TensorProductConvLayer(nn.Module):
         return ops.tpconv_finalize(sum_buf, cnt_buf, reduce == 'mean', scale, shift, res)
 
 
-class OldTensorProductConvLayer(nn.Module):
-    def __init__(self, *a, **k):
-        super().__init__()
-        raise NotImplementedError("OldTensorProductConvLayer (confidence model, SURVEY.md row f2) is not built yet")
+class OldTensorProductConvLayer(TensorProductConvLayer):
+    """Drop-in for models/tensor_layers.py:338-380 (the confidence model's layer): one radial MLP, same kernels as the new
+    layer.  The reference's 100 000-edge chunking only bounds memory (all chunks share the MLP) and is not reproduced;
+    the residual is added BEFORE the BatchNorm (:371-376), unlike the new layer."""
+
+    def __init__(self, in_irreps, sh_irreps, out_irreps, n_edge_features, residual=True, batch_norm=True, dropout=0.0,
+                 hidden_features=None):
+        super().__init__(in_irreps, sh_irreps, out_irreps, n_edge_features, residual=residual, batch_norm=batch_norm,
+                         dropout=dropout, hidden_features=hidden_features, faster=False, edge_groups=1,
+                         tp_weights_layers=2, activation='relu')
+
+    @torch.no_grad()
+    def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0,
+                edge_vec=None, assume_sorted=False, gather_scalars=0):
+        if not self.residual:
+            return super().forward(node_attr, edge_index, edge_attr, edge_sh, out_nodes, reduce, edge_weight,
+                                   edge_vec=edge_vec, assume_sorted=assume_sorted, gather_scalars=gather_scalars)
+        bn, self.batch_norm, self.residual = self.batch_norm, None, False        # conv only, then residual -> BatchNorm
+        try:
+            out = super().forward(node_attr, edge_index, edge_attr, edge_sh, out_nodes, reduce, edge_weight,
+                                  edge_vec=edge_vec, assume_sorted=assume_sorted, gather_scalars=gather_scalars)
+        finally:
+            self.batch_norm, self.residual = bn, True
+        out = out + F.pad(node_attr, (0, out.shape[-1] - node_attr.shape[-1]))
+        if bn is not None:
+            scale, shift = bn.fold()
+            out = out * scale + shift
+        return out.to(node_attr.dtype)

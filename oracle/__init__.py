@@ -28,6 +28,8 @@ Pinning status
 The reference ships no tests, golden vectors or fixtures for this path.
 What pins this oracle:
 
+0. Files: e3nn_lite / graph_ops (third-party semantics), layers / tensor_layers / cg_model (score model),
+   old_cg_model (confidence model, models/old_cg_model.py), diffusion / sampling (sampler), tables, ref_shims.
 1. In-tree reference code run in the authoring container: ``tests/golden/make_golden.py``
    imports the UNMODIFIED reference modules (models/layers.py, models/tensor_layers.py,
    models/cg_model.py, utils/geometry.py, utils/diffusion_utils.py, utils/torsion.py,

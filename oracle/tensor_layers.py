@@ -138,3 +138,33 @@ class TensorProductConvLayer(nn.Module):
         if self.residual:
             out = out + F.pad(node_attr, (0, out.shape[-1] - node_attr.shape[-1]))
         return out.to(dt)
+
+
+class OldTensorProductConvLayer(nn.Module):
+    """models/tensor_layers.py:338-380: one radial MLP, tensor product + scatter (the reference's 100 000-edge chunking
+    shares that MLP, so it only bounds memory), then the residual BEFORE the BatchNorm (the new layer adds it after)."""
+
+    def __init__(self, in_irreps, sh_irreps, out_irreps, n_edge_features, residual=True, batch_norm=True, dropout=0.0,
+                 hidden_features=None):
+        super().__init__()
+        self.in_irreps, self.out_irreps, self.sh_irreps, self.residual = in_irreps, out_irreps, sh_irreps, residual
+        hidden_features = n_edge_features if hidden_features is None else hidden_features
+        self.tp = o3.FullyConnectedTensorProduct(in_irreps, sh_irreps, out_irreps, shared_weights=False)
+        self.fc = nn.Sequential(nn.Linear(n_edge_features, hidden_features), nn.ReLU(), nn.Dropout(dropout),
+                                nn.Linear(hidden_features, self.tp.weight_numel))
+        self.batch_norm = o3.BatchNorm(out_irreps) if batch_norm else None
+
+    def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0):
+        tgt, src = edge_index[0], edge_index[1]
+        n_out = int(out_nodes or node_attr.shape[0])
+        w = self.fc(edge_attr) * edge_weight
+        summed = scatter(self.tp(node_attr[src], edge_sh, w), tgt, dim=0, dim_size=n_out, reduce='sum')
+        if reduce == 'mean':     # tp_scatter_multigroup, :227-229
+            cnt = torch.bincount(tgt, minlength=n_out).to(summed.dtype)
+            summed = summed / torch.clamp(cnt, torch.finfo(summed.dtype).eps)[:, None]
+        out = summed
+        if self.residual:
+            out = out + F.pad(node_attr, (0, out.shape[-1] - node_attr.shape[-1]))
+        if self.batch_norm:
+            out = self.batch_norm(out)
+        return out.to(node_attr.dtype)

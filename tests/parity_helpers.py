@@ -155,3 +155,26 @@ def golden_model(case, which):
     m.load_state_dict(case['state'], strict=True)
     poses = [graph_from_dict(d) for d in case['poses']]
     return m.to(dev), poses, a
+
+
+def golden_confidence_model(case, which):
+    """Confidence model ('oracle' on CPU | 'product' on cuda:0) + pose list rebuilt from a ref_confidence.pt case."""
+    from functools import partial
+    from diffdock_b200.hetero import graph_from_dict
+    from diffdock_b200.synthetic import default_model_args
+    a = default_model_args()
+    if which == 'oracle':
+        from oracle.old_cg_model import CGOldModel
+        from oracle.layers import get_timestep_embedding
+        from oracle.diffusion import t_to_sigma
+        dev = 'cpu'
+    else:
+        from diffdock_b200.old_cg_model import CGOldModel
+        from diffdock_b200.diffusion_utils import get_timestep_embedding, t_to_sigma
+        dev = torch.device('cuda:0')
+    kw = dict(case['kw'])
+    if case['lm_dim']:
+        kw['lm_embedding_dim'] = case['lm_dim']     # the fixture shrinks the 1280-wide LM embedding to 16 columns
+    m = CGOldModel(partial(t_to_sigma, args=a), dev, get_timestep_embedding('sinusoidal', 8, a.embedding_scale), **kw).eval()
+    m.load_state_dict(case['state'], strict=True)
+    return m.to(dev), [graph_from_dict(d) for d in case['poses']]

@@ -1,0 +1,80 @@
+"""GPU parity of the confidence model: diffdock_b200.old_cg_model.CGOldModel vs the reference
+fixture (models/old_cg_model.py run unmodified, tests/golden/make_golden_confidence.py) and vs the CPU oracle."""
+import copy
+from functools import partial
+
+import pytest
+import torch
+
+from diffdock_b200.hetero import collate
+from tests.parity_helpers import golden_confidence_model, golden_model, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _confidence(m, poses, dev):
+    from diffdock_b200.diffusion_utils import set_time
+    b = collate(copy.deepcopy(poses)).to(dev)
+    set_time(b, 0, 0, 0, 0, len(poses), False, dev)
+    return m(b).float().cpu()
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_confidence_matches_reference_fixture(built_lib, idx):
+    case = load_golden('ref_confidence.pt')[idx]
+    m, poses = golden_confidence_model(case, 'product')
+    conf = _confidence(m, poses, torch.device('cuda:0'))
+    ref = case['confidence']
+    assert conf.shape == ref.shape
+    assert (conf - ref).abs().max() < 1e-4 * max(1.0, float(ref.abs().max())), (conf, ref)     # tolerance: 1e-4 relative
+
+
+def test_confidence_full_width_matches_oracle(built_lib):
+    """DiffDock-L-sized widths (ns=48, nv=10: the fully fused tcgen05 path) on a 60-residue complex, against the oracle."""
+    from oracle.diffusion import set_time as o_set_time, t_to_sigma as o_t2s
+    from oracle.layers import get_timestep_embedding as o_temb
+    from oracle.old_cg_model import CGOldModel as OModel
+    from diffdock_b200.diffusion_utils import get_timestep_embedding, t_to_sigma
+    from diffdock_b200.old_cg_model import CGOldModel
+    from diffdock_b200.synthetic import default_model_args, make_pose_list
+    from tests.parity_helpers import rand_bn_
+    a = default_model_args()
+    kw = dict(sigma_embed_dim=16, sh_lmax=2, ns=48, nv=10, num_conv_layers=4, cross_max_distance=30.0,
+              distance_embed_dim=16, cross_distance_embed_dim=16, lm_embedding_type='esm', lm_embedding_dim=32,
+              confidence_mode=True, use_old_atom_encoder=True)
+    torch.manual_seed(5)
+    mo = OModel(partial(o_t2s, args=a), 'cpu', o_temb('sinusoidal', 16, a.embedding_scale), **kw).eval()
+    g = torch.Generator().manual_seed(6)
+    for mod in mo.modules():
+        if mod.__class__.__name__ in ('BatchNorm', 'BatchNorm1d'):
+            rand_bn_(mod, g)
+    mp = CGOldModel(partial(t_to_sigma, args=a), torch.device('cuda:0'),
+                    get_timestep_embedding('sinusoidal', 16, a.embedding_scale), **kw).eval()
+    mp.load_state_dict(mo.state_dict(), strict=True)
+    mp = mp.to('cuda:0')
+    poses = make_pose_list(4, n_res=60, n_atoms=14, seed=77, tr_sigma_max=1.0, lm_dim=32)
+    b = collate(copy.deepcopy(poses))
+    o_set_time(b, 0, 0, 0, len(poses), 'cpu')
+    with torch.no_grad():
+        ref = mo(b)
+    conf = _confidence(mp, poses, torch.device('cuda:0'))
+    assert (conf - ref).abs().max() < 1e-4 * max(1.0, float(ref.abs().max())), (conf, ref)
+
+
+def test_sampling_returns_confidence(built_lib):
+    """sampling(confidence_model=...) ranks the final poses like utils/sampling.py:208-227: the confidences it returns
+    equal the confidence model applied to the returned poses."""
+    from diffdock_b200.diffusion_utils import get_t_schedule, t_to_sigma
+    from diffdock_b200.sampling import sampling
+    case = load_golden('ref_cg_model.pt')[0]
+    score, poses, a = golden_model(case, 'product')
+    ccase = load_golden('ref_confidence.pt')[0]
+    conf_model, _ = golden_confidence_model(ccase, 'product')
+    sched = get_t_schedule('expbeta', 3)
+    torch.manual_seed(0)
+    out, conf = sampling(copy.deepcopy(poses), score, 3, sched, sched, sched, 'cuda:0', partial(t_to_sigma, args=a), a,
+                         batch_size=3, no_final_step_noise=True, confidence_model=conf_model,
+                         confidence_data_list=copy.deepcopy(poses), confidence_model_args=a)
+    assert conf.shape == (3,) and torch.isfinite(conf).all()
+    again = _confidence(conf_model, [d.to('cpu') if hasattr(d, 'to') else d for d in out], torch.device('cuda:0'))
+    assert (conf.cpu() - again).abs().max() < 1e-5

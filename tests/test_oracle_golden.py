@@ -87,6 +87,21 @@ def test_cg_model_matches_reference(idx):
     assert rel_err(tr, case['tr']) < TOL and rel_err(rot, case['rot']) < TOL and rel_err(tor, case['tor']) < TOL
 
 
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_confidence_model_matches_reference(idx):
+    """oracle/old_cg_model.py vs the reference's models/old_cg_model.py CGOldModel(confidence_mode) (fixture)."""
+    from oracle.diffusion import set_time
+    from tests.parity_helpers import golden_confidence_model
+    case = load_golden('ref_confidence.pt')[idx]
+    m, poses = golden_confidence_model(case, 'oracle')
+    b = collate(poses)
+    set_time(b, 0, 0, 0, len(poses), 'cpu')
+    with torch.no_grad():
+        conf = m(b)
+    assert conf.shape == case['confidence'].shape
+    assert (conf - case['confidence']).abs().max() < 1e-5 * max(1.0, float(case['confidence'].abs().max()))
+
+
 def test_conformer_update_matches_reference():
     from oracle.diffusion import modify_conformer_batch
     c = load_golden('ref_conformer.pt')
