@@ -66,7 +66,7 @@ def layer_parity_case(seed=0, n_nodes=64, n_edges=700, ns=48, nv=10, lmax=2, sta
     return rel_err(got, ref)
 
 
-def make_model_pair(args, seed=0, lm=True):
+def make_model_pair(args, seed=0, lm=True, product=True):
     """(oracle CGModel on CPU, product CGModel) sharing one random state_dict (BatchNorm statistics randomised)."""
     from functools import partial
     from oracle.cg_model import CGModel as OModel
@@ -90,23 +90,31 @@ def make_model_pair(args, seed=0, lm=True):
     for m in o.modules():
         if m.__class__.__name__ == 'BatchNorm':
             rand_bn_(m, gen)
+    if not product:
+        return o, None
     p = PModel(partial(p_t2s, args=args), torch.device('cuda:0'),
                p_emb('sinusoidal', args.sigma_embed_dim, args.embedding_scale), **kw).eval()
     p.load_state_dict(o.state_dict(), strict=True)     # includes e3nn-style tp.* buffers, which must be accepted
     return o, p.to('cuda:0')
 
 
-def model_parity_case(seed=0, lmax=2, ns=16, nv=4, n_layers=3, emb=16, n_res=60, n_atoms=12, n_poses=3, t=0.5, **over):
+def model_parity_case(seed=0, lmax=2, ns=16, nv=4, n_layers=3, emb=16, n_res=60, n_atoms=12, n_poses=3, t=0.5,
+                      far_poses=(), run_product=True, **over):
     from diffdock_b200.synthetic import default_model_args, make_pose_list
     from diffdock_b200.hetero import collate
     from oracle.diffusion import set_time
     args = default_model_args(ns=ns, nv=nv, sh_lmax=lmax, num_conv_layers=n_layers, distance_embed_dim=emb,
                               cross_distance_embed_dim=emb, sigma_embed_dim=emb, **over)
-    o, p = make_model_pair(args, seed)
+    o, p = make_model_pair(args, seed, product=run_product)
     poses = make_pose_list(n_poses, n_res=n_res, n_atoms=n_atoms, seed=seed + 3, tr_sigma_max=args.tr_sigma_max * t)
+    for i in far_poses:       # ligand moved out of every cross cut-off: that complex has no ligand-receptor edges
+        poses[i]['ligand'].pos = poses[i]['ligand'].pos + 500.0
     g_cpu = collate(poses)
-    g_gpu = collate(poses).to('cuda:0')
     set_time(g_cpu, t, t, t, n_poses, 'cpu')
+    if not run_product:
+        with torch.no_grad():
+            return o(g_cpu)
+    g_gpu = collate(poses).to('cuda:0')
     set_time(g_gpu, t, t, t, n_poses, 'cuda:0')
     with torch.no_grad():
         ref = o(g_cpu)

@@ -24,3 +24,13 @@ def test_scores_match_oracle_cfg_l2(built_lib, t):
 def test_no_rotatable_bonds_branch(built_lib):
     errs = model_parity_case(seed=2, lmax=2, ns=16, nv=4, n_layers=2, emb=16, n_res=40, n_atoms=3, n_poses=2, t=0.3)
     assert errs['tor_numel'] == 0 and max(errs['tr'], errs['rot']) < TOL, errs
+
+
+@pytest.mark.parametrize("far", [(1,), (0, 1, 2)])
+def test_complexes_without_cross_edges(built_lib, far):
+    """Ligands outside every ligand-receptor cut-off: some / all complexes contribute no cross edges (empty edge groups,
+    receptor nodes with no incoming ligand message)."""
+    errs = model_parity_case(seed=4, lmax=2, ns=16, nv=4, n_layers=2, emb=16, n_res=40, n_atoms=8, n_poses=3, t=0.3,
+                             far_poses=far)
+    errs.pop('tor_numel', None)
+    assert max(errs.values()) < TOL, errs
