@@ -234,6 +234,7 @@ struct FusedParams {
   const float* vec; const float* ew; int lmax;
   float* sum; int d_out; float* cnt;
   long long n_edges;
+  int seg_flush;                                     // segmented-shuffle scatter (1) or one atomic per lane and value (0)
   int dbg_noload;                                    // diagnostics: skip the B copies (timing only, results garbage)
   unsigned long long* dbg;                           // optional [16] clock counters (DDB200_FUSED_DEBUG=1), else nullptr
 };
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
       // runs of equal scatter targets inside the warp (rows past the end sort last)
       const int seg_key = valid ? dst_e : 0x7fffffff;
       const int key_dn = __shfl_down_sync(0xffffffffu, seg_key, 1), key_up = __shfl_up_sync(0xffffffffu, seg_key, 1);
-      const bool seg_sorted = __all_sync(0xffffffffu, lane == 31 || key_dn >= seg_key);
+      const bool seg_sorted = p.seg_flush && __all_sync(0xffffffffu, lane == 31 || key_dn >= seg_key);
       const bool seg_head = lane == 0 || key_up != seg_key;
       uint32_t seg_same = 0;      // bit o: lane + 2^o belongs to the same run
 #pragma unroll
@@ -769,6 +770,8 @@ extern "C" int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, 
   p.x = x; p.ld_x = ld_x; p.vec = edge_vec; p.ew = edge_weight; p.lmax = sh_lmax; p.sum = sum; p.d_out = d_out; p.cnt = cnt;
   p.n_edges = n_edges;
   p.dbg = fused_debug_buffer();
+  static const int seg_env = [] { const char* e = getenv("DDB200_FUSED_SEGFLUSH"); return e ? atoi(e) : 1; }();
+  p.seg_flush = seg_env;
   static const int noload = [] { const char* e = getenv("DDB200_FUSED_NOLOAD"); return e ? atoi(e) : 0; }();
   p.dbg_noload = p.dbg ? noload : 0;
   const int n_kb_max = n_kb > n_kb1 ? n_kb : n_kb1;
