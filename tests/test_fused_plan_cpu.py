@@ -1,0 +1,110 @@
+"""Host logic of the fully fused convolution (diffdock_b200/fused.py): a numpy/torch emulation that reads ONLY the plan the
+kernel reads (swizzled bf16 operand images with folded biases, tile table, Clebsch-Gordan term tables) must reproduce
+the oracle layer.  Pins the image layout, the split-bf16 scheme and the tile/accumulator bookkeeping without a GPU."""
+import math
+
+import pytest
+import torch
+
+from diffdock_b200 import fused
+from diffdock_b200.tensor_layers import get_irrep_seq
+from diffdock_b200.tp_table import build_table
+
+KINDS = {0: (48, 1, 4), 1: (10, 3, 16), 2: (16, 1, 8), 3: (4, 3, 16)}     # kind -> (mul_out, 2l_out+1, rows per tile)
+
+
+def _deswizzle(img):
+    """[T, n_kb, 256, 8, 8] 128B-swizzled -> [T, 256, n_kb*64] row-major (the swizzle is an involution)."""
+    T, n_kb, R = img.shape[:3]
+    rows = torch.arange(R) % 8
+    src = torch.arange(8)[None, :] ^ rows[:, None]
+    lin = torch.gather(img, 3, src[None, None, :, :, None].expand(T, n_kb, R, 8, 8))
+    return lin.permute(0, 2, 1, 3, 4).reshape(T, R, n_kb * 64).double()
+
+
+def _split_operand(a, kpad):
+    """fp32 activations [E, K] -> the kernel's A image [hi | hi | lo | 1 1 | 0...] as float64."""
+    hi = a.to(torch.bfloat16)
+    lo = (a - hi.float()).to(torch.bfloat16)
+    E, K = a.shape
+    out = torch.zeros(E, kpad, dtype=torch.float64)
+    out[:, :K], out[:, K:2 * K], out[:, 2 * K:3 * K] = hi.double(), hi.double(), lo.double()
+    out[:, 3 * K:3 * K + 2] = 1.0
+    return out
+
+
+def _sh(vec):
+    v = torch.nn.functional.normalize(vec.double(), dim=-1)
+    x, y, z = v[:, 0], v[:, 1], v[:, 2]
+    s3, s5, s15 = math.sqrt(3), math.sqrt(5), math.sqrt(15)
+    return torch.stack([torch.ones_like(x), s3 * x, s3 * y, s3 * z, s15 * x * z, s15 * x * y,
+                        s5 * (y * y - 0.5 * (x * x + z * z)), s15 * y * z, 0.5 * s15 * (z * z - x * x)], 1)
+
+
+def emulate(plan, ea, node, ns, tgt, src, x, vec, n_out, ew=None):
+    E = ea.shape[0]
+    a0 = torch.cat([ea, node[tgt, :ns], node[src, :ns]], 1) if ns else ea
+    n_kb1, n_kb = plan.w1_images.shape[1], plan.w2_images.shape[1]
+    w1 = _deswizzle(plan.w1_images)[0]                                   # [256, K1']
+    H = plan.hidden
+    hid = torch.relu(_split_operand(a0, n_kb1 * 64) @ w1[:H].T).float()  # fp32 accumulator -> ReLU
+    A = _split_operand(hid, n_kb * 64)
+    w2 = _deswizzle(plan.w2_images)                                      # [T, 256, K']
+    Y = _sh(vec)
+    tiles, ment = plan.tiles.tolist(), plan.ment.reshape(-1, 2).tolist()
+    ty, tv = plan.term_y.tolist(), plan.term_v.double()
+    out = torch.zeros(n_out, plan.table.d_out, dtype=torch.float64)
+    acc = None
+    for t, (kind, n_mma, x_off, nrow, d_in, out_off, flags, ment_off) in enumerate(tiles):
+        mul_out, dout, rows = KINDS[kind]
+        assert n_mma == mul_out * rows and n_mma % 16 == 0 and n_mma <= 192
+        Wt = A @ w2[t, :n_mma].T                                         # [E, N]: the TMEM accumulator tile
+        M = torch.zeros(E, 3, 3, dtype=torch.float64)
+        for i in range(d_in):
+            for k in range(dout):
+                b, n = ment[ment_off + i * dout + k]
+                for q in range(b, b + n):
+                    M[:, i, k] += tv[q] * Y[:, ty[q]]
+        if ew is not None:
+            M = M * ew.double().reshape(-1, 1, 1)
+        xs = torch.zeros(E, rows, d_in, dtype=torch.float64)
+        xs[:, :nrow] = x[src][:, x_off:x_off + nrow * d_in].double().reshape(E, nrow, d_in)
+        z = torch.einsum('eri,eik->erk', xs, M[:, :d_in, :dout])         # [E, rows, dout]
+        if flags & 1:
+            acc = torch.zeros(E, mul_out, dout, dtype=torch.float64)
+        acc = acc + torch.einsum('erw,erk->ewk', Wt.reshape(E, rows, mul_out), z)
+        if flags & 2:
+            full = torch.zeros(E, plan.table.d_out, dtype=torch.float64)
+            full[:, out_off:out_off + mul_out * dout] = acc.reshape(E, -1)
+            out.index_add_(0, tgt, full)
+    return out
+
+
+@pytest.mark.parametrize("li", [0, 1, 2, 3])
+def test_fused_plan_emulation_matches_oracle_layer(li):
+    from oracle.tensor_layers import TensorProductConvLayer as OLayer
+    ns, nv = 48, 10
+    seq = get_irrep_seq(ns, nv, False, False)
+    ins, outs, shs = seq[min(li, 3)], seq[min(li + 1, 3)], '1x0e+1x1o+1x2e'
+    torch.manual_seed(li)
+    layer = OLayer(ins, shs, outs, 3 * ns, residual=False, batch_norm=False, hidden_features=3 * ns).eval()
+    table = build_table(ins, shs, outs, 'fctp')
+    assert fused.supported(table, 3 * ns, 3 * ns)
+    plan = fused.FusedPlan(table, layer.fc[0].weight, layer.fc[0].bias, layer.fc[-1].weight, layer.fc[-1].bias)
+    g = torch.Generator().manual_seed(100 + li)
+    n_nodes, E = 11, 150
+    x = torch.randn(n_nodes, table.d_in, generator=g)
+    tgt = torch.sort(torch.randint(0, n_nodes, (E,), generator=g)).values
+    src = torch.randint(0, n_nodes, (E,), generator=g)
+    vec = torch.randn(E, 3, generator=g)
+    ea = torch.randn(E, ns, generator=g)
+    ew = torch.rand(E, 1, generator=g)
+    from oracle import e3nn_lite as o3
+    sh = o3.spherical_harmonics(o3.Irreps(shs), vec, normalize=True, normalization='component')
+    ea_full = torch.cat([ea, x[tgt, :ns], x[src, :ns]], 1)
+    with torch.no_grad():
+        ref = layer(x, torch.stack([tgt, src]), ea_full, sh, reduce='sum', edge_weight=ew)
+    got = emulate(plan, ea, x, ns, tgt, src, x, vec, n_nodes, ew)
+    err = float((got - ref.double()).abs().max() / ref.abs().max())
+    assert err < 3e-5, err          # split-bf16 x3: ~2^-16 relative per product, fp32-level after accumulation
+    assert plan.n_tiles == len(plan.tiles) and plan.mma_flops_per_tile > 0
