@@ -1,14 +1,15 @@
 // Fully fused equivariant convolution for one edge group (sm_100a): radial MLP on tcgen05 + tensor-product contraction
 // straight out of tensor memory + scatter - the per-edge weight tensor [E, weight_numel] never exists in HBM.
 //
-//   for a tile of 128 CSR-sorted edges (one CTA, persistent over tiles):
+//   for a unit of 256 CSR-sorted edges (a CTA pair on tcgen05 cta_group::2, 128 edges = 128 TMEM lanes per CTA, persistent
+//   over units; CG = 1: one CTA per 128-edge tile):
 //     A0' = split-bf16([edge_attr | node[tgt,:ns] | node[src,:ns] | 1 1])      built in shared memory (128B swizzle)
 //     H   = relu(A0' x W1'^T)          tcgen05.mma -> TMEM -> registers -> A' image (bias folded via the ones columns)
-//     for every N tile (whole rows u of one path block [mul_in, mul_out], <= 256 columns):
+//     for every N tile (whole rows u of one path block [mul_in, mul_out], <= 192 columns):
 //        Wt = A' x W2'^T[tile]         tcgen05.mma into one of two TMEM accumulators   (B' images streamed by TMA bulk copies)
 //        consumer thread e (= TMEM lane): acc[w,k] += Wt[e, (u,w)] * z_e[u,k],   z_e[u,k] = sum_i x[src_e][u,i] M_e[i,k],
 //                                         M_e = edge_weight * coef * C . Y(vec_e)       (tcgen05.ld 32x32b.x32 + FFMA)
-//     at the end of an output irrep: sum[tgt_e, irrep] += acc  (warp pre-reduction when the 32 lanes share the target)
+//     at the end of an output irrep: sum[tgt_e, irrep] += acc  (segmented warp reduction over runs of equal targets)
 //
 // Replaces models/tensor_layers.py:139-144 / :204-221 *including* the FCBlock at :140/:211 and the edge_attr_ assembly of
 // models/cg_model.py:342-349.  Plan (tiles, operand images, CG terms) is built by diffdock_b200/fused.py.
@@ -38,9 +39,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -67,12 +65,6 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {  
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -138,30 +130,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
 // LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
-// layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-template <int CG>
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if constexpr (CG == 1)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  else   // M = 256: rows 0-127 from the leader CTA's A image / TMEM, rows 128-255 from its peer; each CTA holds N/2 rows of B
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-// descriptor passed as its low word (address field + LBO) - the high word is the constant (SBO 1024 B, version 1,
-// SWIZZLE_128B): the issuing loop then only adds small offsets to one 32-bit value per operand
+// layout type SWIZZLE_128B = 2 in [61,64).  The descriptor is passed as its low word (address field + LBO); the high word
+// is a constant, so the issuing loop only adds small offsets to one 32-bit value per operand.
+// M = 256 (pair): rows 0-127 come from the leader CTA's A image / go to its TMEM, rows 128-255 from / to its peer; each CTA
+// holds N/2 rows of B.
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
 template <int CG>
