@@ -181,6 +181,8 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 cg = collate(copy.deepcopy(conf_batches[batch_id]))
                 cg['ligand'].pos = g['ligand'].pos.cpu()
                 cg = cg.to(device)
+                if getattr(confidence_model_args, 'crop_beyond', None) is not None:     # utils/sampling.py:213-217
+                    cg = crop_receptor(cg, confidence_model_args.crop_beyond)
                 set_time(cg, 0, 0, 0, 0, b, confidence_model_args.all_atoms, device)
                 out = confidence_model(cg)
             else:

@@ -1,5 +1,5 @@
-"""Oracle restatement of the reverse-diffusion loop utils/sampling.py:69-201 (no confidence model, no
-visualisation).  TEST INFRASTRUCTURE."""
+"""Oracle restatement of the reverse-diffusion loop utils/sampling.py:69-231 including the confidence-model call after
+the last step (:208-227; no visualisation).  TEST INFRASTRUCTURE."""
 import numpy as np
 import torch
 
@@ -20,7 +20,8 @@ def _triple(v):
 
 def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma,
              model_args, no_random=False, ode=False, batch_size=32, no_final_step_noise=False,
-             temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5, noise_fn=None):
+             temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5, noise_fn=None, confidence_model=None,
+             confidence_data_list=None, confidence_model_args=None):
     """noise_fn(kind, shape) -> tensor replaces torch.normal when given (injected-noise parity runs); otherwise
     torch.normal is called in the reference's order (tr, rot, tor per step), so a shared torch.manual_seed
     reproduces the reference's CPU draws."""
@@ -36,6 +37,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             return noise_fn(kind, shape).to(device)
         return torch.normal(mean=0, std=1, size=shape, device=device)
 
+    confidence = []
     with torch.no_grad():
         for b0 in range(0, N, batch_size):
             chunk = data_list[b0:b0 + batch_size]
@@ -99,4 +101,22 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                                                          tor_perturb if not a.no_torsion else None, mask_rotate)
             for i in range(b):
                 data_list[b0 + i]['ligand'].pos = g['ligand'].pos[i * n:n * (i + 1)]
+            if confidence_model is not None:                                     # utils/sampling.py:208-227
+                if confidence_data_list is not None:
+                    cl = copy.deepcopy(confidence_data_list[b0:b0 + batch_size])
+                    cg = collate(cl)
+                    cg['ligand'].pos = g['ligand'].pos.cpu()
+                    cb = getattr(confidence_model_args, 'crop_beyond', None)
+                    if cb is not None:                                           # :213-217, per complex
+                        parts = cg.to_data_list()
+                        for part in parts:
+                            crop_beyond(part, cb)
+                        cg = collate(parts)
+                    set_time(cg, 0, 0, 0, b, device)
+                    out = confidence_model(cg)
+                else:
+                    out = confidence_model(g)
+                confidence.append(out[0] if type(out) is tuple else out)
+    if confidence_model is not None:
+        return data_list, torch.nan_to_num(torch.cat(confidence, dim=0), nan=-1000)
     return data_list, None

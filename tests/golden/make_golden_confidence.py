@@ -57,3 +57,47 @@ def case(seed, num_conv_layers, dynamic, n_poses=3, lm=True, smooth=False):
 cases = [case(30, 3, False), case(31, 2, True, smooth=True), case(32, 4, False, lm=False)]
 torch.save(cases, os.path.join(OUT, 'ref_confidence.pt'))
 print('ref_confidence.pt', os.path.getsize(os.path.join(OUT, 'ref_confidence.pt')) // 1024, 'KiB')
+
+
+# ------------------------------------------------------------------------------------------------ sampling + confidence
+# utils/sampling.py run unmodified: 3 reverse-diffusion steps of the score model of ref_cg_model.pt[0], then the confidence
+# model of case 0 above on the final poses (confidence_data_list path, with and without confidence crop_beyond).
+import numpy as np                           # noqa: E402
+import utils.sampling as r_sampling         # noqa: E402
+import models.cg_model as r_cg              # noqa: E402
+from argparse import Namespace              # noqa: E402
+from diffdock_b200.hetero import graph_from_dict   # noqa: E402
+
+score_case = torch.load(os.path.join(OUT, 'ref_cg_model.pt'), weights_only=False)[0]
+sa = Namespace(**score_case['args'])
+score = r_cg.CGModel(partial(r_du.t_to_sigma, args=sa), torch.device('cpu'),
+                     r_du.get_timestep_embedding('sinusoidal', 8, sa.embedding_scale), **score_case['kw']).eval()
+score.rec_node_embedding.additional_features_dim = 16
+score.rec_node_embedding.additional_features_embedder = torch.nn.Linear(16 + 6, 6)
+score.load_state_dict(score_case['state'], strict=True)
+poses = [graph_from_dict(d) for d in score_case['poses']]
+
+ca = default_model_args()
+ckw = cases[0]['kw']
+conf = r_old.CGOldModel(partial(r_du.t_to_sigma, args=ca), torch.device('cpu'),
+                        r_du.get_timestep_embedding('sinusoidal', 8, ca.embedding_scale), **ckw).eval()
+conf.rec_node_embedding.lm_embedding_dim = 16
+conf.rec_node_embedding.lm_embedding_layer = torch.nn.Linear(16 + 6, 6)
+conf.load_state_dict(cases[0]['state'], strict=True)
+
+sched = np.array([0.30, 0.18, 0.07])
+runs = []
+for crop in (None, 9.0):
+    cargs = Namespace(all_atoms=False, crop_beyond=crop)
+    torch.manual_seed(77)
+    margs = copy.deepcopy(sa)
+    out_list, c = r_sampling.sampling(data_list=copy.deepcopy(poses), model=score, inference_steps=3, tr_schedule=sched,
+                                      rot_schedule=sched, tor_schedule=sched, device=torch.device('cpu'),
+                                      t_to_sigma=partial(r_du.t_to_sigma, args=sa), model_args=margs, batch_size=3,
+                                      no_final_step_noise=True, confidence_model=conf,
+                                      confidence_data_list=copy.deepcopy(poses), confidence_model_args=cargs)
+    print('crop', crop, 'confidence', c)
+    runs.append(dict(crop_beyond=crop, confidence=c, final_pos=[d['ligand'].pos.clone() for d in out_list]))
+torch.save(dict(score_case=0, confidence_case=0, seed=77, schedule=sched, runs=runs),
+           os.path.join(OUT, 'ref_sampling_confidence.pt'))
+print('ref_sampling_confidence.pt written')

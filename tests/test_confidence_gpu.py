@@ -78,3 +78,27 @@ def test_sampling_returns_confidence(built_lib):
     assert conf.shape == (3,) and torch.isfinite(conf).all()
     again = _confidence(conf_model, [d.to('cpu') if hasattr(d, 'to') else d for d in out], torch.device('cuda:0'))
     assert (conf.cpu() - again).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("run", [0, 1])
+def test_sampling_with_confidence_matches_reference_fixture(built_lib, run):
+    """Product sampling() + confidence model vs the reference's utils/sampling.py run (fixture): final poses and ranking
+    scores, without and with confidence_model_args.crop_beyond (device-side crop_receptor instead of the reference's
+    to_data_list / crop / re-collate)."""
+    from argparse import Namespace
+    from diffdock_b200.diffusion_utils import t_to_sigma
+    from diffdock_b200.sampling import sampling
+    s = load_golden('ref_sampling_confidence.pt')
+    r = s['runs'][run]
+    score, poses, a = golden_model(load_golden('ref_cg_model.pt')[s['score_case']], 'product')
+    conf_model, _ = golden_confidence_model(load_golden('ref_confidence.pt')[s['confidence_case']], 'product')
+    torch.manual_seed(s['seed'])
+    noise = lambda kind, shape: torch.normal(mean=0, std=1, size=shape)           # the reference's CPU draws
+    out, conf = sampling(copy.deepcopy(poses), score, len(s['schedule']), s['schedule'], s['schedule'], s['schedule'],
+                         'cuda:0', partial(t_to_sigma, args=a), a, batch_size=3, no_final_step_noise=True,
+                         confidence_model=conf_model, confidence_data_list=copy.deepcopy(poses),
+                         confidence_model_args=Namespace(all_atoms=False, crop_beyond=r['crop_beyond']), noise_fn=noise)
+    for d, ref in zip(out, r['final_pos']):
+        err = float((d['ligand'].pos.cpu() - ref).abs().max() / ref.abs().max())
+        assert err < 1e-4, err
+    assert (conf.cpu() - r['confidence']).abs().max() < 1e-4, (conf, r['confidence'])

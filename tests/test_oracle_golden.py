@@ -102,6 +102,26 @@ def test_confidence_model_matches_reference(idx):
     assert (conf - case['confidence']).abs().max() < 1e-5 * max(1.0, float(case['confidence'].abs().max()))
 
 
+@pytest.mark.parametrize("run", [0, 1])
+def test_sampling_with_confidence_model_matches_reference(run):
+    """oracle sampling() + confidence model (with / without confidence_model_args.crop_beyond) vs utils/sampling.py:208-227."""
+    from oracle.sampling import sampling
+    from oracle.diffusion import t_to_sigma
+    from tests.parity_helpers import golden_confidence_model
+    s = load_golden('ref_sampling_confidence.pt')
+    r = s['runs'][run]
+    score, poses, a = golden_model(load_golden('ref_cg_model.pt')[s['score_case']], 'oracle')
+    conf, _ = golden_confidence_model(load_golden('ref_confidence.pt')[s['confidence_case']], 'oracle')
+    torch.manual_seed(s['seed'])
+    out, c = sampling(copy.deepcopy(poses), score, len(s['schedule']), s['schedule'], s['schedule'], s['schedule'], 'cpu',
+                      partial(t_to_sigma, args=a), a, batch_size=3, no_final_step_noise=True, confidence_model=conf,
+                      confidence_data_list=copy.deepcopy(poses),
+                      confidence_model_args=Namespace(all_atoms=False, crop_beyond=r['crop_beyond']))
+    for d, ref in zip(out, r['final_pos']):
+        assert rel_err(d['ligand'].pos, ref) < 1e-4
+    assert (c - r['confidence']).abs().max() < 1e-5, (c, r['confidence'])
+
+
 def test_conformer_update_matches_reference():
     from oracle.diffusion import modify_conformer_batch
     c = load_golden('ref_conformer.pt')
