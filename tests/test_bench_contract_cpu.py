@@ -25,3 +25,17 @@ def test_reference_arm_json_line():
     assert cb['kind'] in ('port', 'reference') and cb['cores'] == 4 and cb['value'] == d['value'] and cb['sample']
     e = d['e2e']
     assert e['value'] == d['value'] and e['unit'] == d['unit'] and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: rank 0 alone runs and prints the reference line, the other ranks exit 0 without work."""
+    env = dict(os.environ, DDB200_CPU_THREADS='2')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29547', os.path.join(ROOT, 'bench.py'),
+                          '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '1', '--n-res', '40',
+                          '--n-atoms', '8', '--poses', '2'], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['n_gpus'] == 2
