@@ -1,6 +1,8 @@
 """Multi-GPU driver: poses / complexes are independent units, so each rank samples a contiguous
 block with no collective inside the step loop; ONE all_gather of the final ligand coordinates at the end
-(NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+(NCCL over NVLink on GPUs; gloo in the CPU tests).  The reference samples the N poses of a complex in one process
+(inference.py:236-262: N deep copies -> utils/sampling.py:sampling); its only data parallelism is PyG DataParallel
+over complexes (utils/utils.py:279), so this module has no reference counterpart to mirror."""
 from __future__ import annotations
 
 from typing import Callable, List, Sequence

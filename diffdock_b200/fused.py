@@ -1,4 +1,6 @@
 """Host side of the fully fused convolution kernel (csrc/fused_conv.cu): per (layer, edge group) plan.
+Replaces, per edge group, the reference's edge_attr_ assembly (models/cg_model.py:342-349), the radial FCBlock
+(models/layers.py:10-17 at models/tensor_layers.py:140,211) and the tensor product + scatter (models/tensor_layers.py:139-144,204-221).
 
 The fused kernel computes, for a tile of 128 edges, the radial MLP on the tcgen05 tensor cores and contracts the resulting
 per-edge tensor-product weights with the edge's irreps *straight out of tensor memory* - the ``[E, weight_numel]`` weight

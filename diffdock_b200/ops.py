@@ -1,4 +1,12 @@
-"""Tensor-level wrappers over the C ABI (device pointers + current CUDA stream).  CUDA tensors only."""
+"""Tensor-level wrappers over the C ABI (device pointers + current CUDA stream).  CUDA tensors only.
+
+What each wrapper stands in for in the reference (details per entry point in include/diffdock_b200.h):
+  tpconv_accumulate / tpconv_finalize   gather + o3.spherical_harmonics + tensor product + torch_scatter.scatter + bincount and
+                                        the mean / BatchNorm / residual epilogue, models/tensor_layers.py:139-144,204-229,327-332
+  radius                                torch_cluster.radius / radius_graph, models/cg_model.py:477,543-548,630
+  segment_ptr                           the CSR row pointer of a sorted ``batch`` vector (PyG ``Batch.ptr``)
+  pose_update                           utils/sampling.py:133-191 + utils/diffusion_utils.py:60-78 (modify_conformer_batch) +
+                                        utils/torsion.py:75-90 + utils/geometry.py:246-276 (Kabsch)"""
 from __future__ import annotations
 
 import ctypes as C
