@@ -108,3 +108,38 @@ def test_fused_plan_emulation_matches_oracle_layer(li):
     err = float((got - ref.double()).abs().max() / ref.abs().max())
     assert err < 3e-5, err          # split-bf16 x3: ~2^-16 relative per product, fp32-level after accumulation
     assert plan.n_tiles == len(plan.tiles) and plan.mma_flops_per_tile > 0
+
+
+def test_fused_plan_tile_flags_and_limits():
+    """Tile table invariants the kernel relies on: N a multiple of 16 and <= 192 (two 8-row halves for a CTA pair), flag 1 on
+    the first / flag 2 on the last tile of every output irrep, flag 4 exactly where the path changes, tiles of one output
+    irrep contiguous."""
+    ns, nv = 48, 10
+    seq = get_irrep_seq(ns, nv, False, False)
+    table = build_table(seq[3], '1x0e+1x1o+1x2e', seq[3], 'fctp')
+    g = torch.Generator().manual_seed(0)
+    H = 3 * ns
+    plan = fused.FusedPlan(table, torch.randn(H, H, generator=g), torch.randn(H, generator=g),
+                           torch.randn(table.weight_numel, H, generator=g), torch.randn(table.weight_numel, generator=g))
+    tiles = plan.tiles.tolist()
+    assert len(tiles) == plan.n_tiles <= 160
+    assert tiles[0][6] & 1 and tiles[0][6] & 4 and tiles[-1][6] & 2
+    seen_out = []
+    for i, (kind, n, x_off, nrow, d_in, out_off, flags, ment) in enumerate(tiles):
+        mul_out, dout, rows = KINDS[kind]
+        assert n == mul_out * rows and n % 16 == 0 and 16 <= n <= 192 and (n // 2) % 8 == 0
+        assert 1 <= nrow <= rows and d_in in (1, 3) and 0 <= x_off and x_off + nrow * d_in <= table.d_in
+        assert out_off + mul_out * dout <= table.d_out
+        if flags & 1:
+            assert out_off not in seen_out, "tiles of one output irrep must be contiguous"
+            seen_out.append(out_off)
+            assert i == 0 or tiles[i - 1][6] & 2
+        else:
+            assert out_off == tiles[i - 1][5] and not (tiles[i - 1][6] & 2)
+        if i and (ment != tiles[i - 1][7] or flags & 1):
+            assert flags & 4 or ment == tiles[i - 1][7]
+        if flags & 4 and i:
+            assert ment != tiles[i - 1][7] or x_off <= tiles[i - 1][2]
+    # every reference weight column is placed exactly once: total valid columns = weight_numel
+    assert sum(t[3] * KINDS[t[0]][0] for t in tiles) == table.weight_numel
+    assert not fused.supported(build_table('16x0e', '1x0e+1x1o+1x2e', '16x0e + 4x1o', 'fctp'), 400, 48)   # hidden too wide
