@@ -151,6 +151,7 @@ class CGModel(nn.Module):
         z = np.load(_TABLES)
         self.register_buffer('_so3_table', torch.from_numpy(z['so3_exp_score_norms']).float(), persistent=False)
         self.register_buffer('_torus_table', torch.from_numpy(z['torus_score_norm']).float(), persistent=False)
+        self._sync_free = None
 
     # ---------------------------------------------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -221,8 +222,39 @@ class CGModel(nn.Module):
         bonds = ll.edge_index[:, mask].long()
         c['bonds'], c['n_bonds'] = bonds, int(bonds.shape[1])
         c['bond_batch'] = lig.batch[bonds[0]] if bonds.shape[1] else None
+        self._static_sync_free(data, c)
         rr._b200 = c
         return c
+
+    def _static_sync_free(self, data, c):
+        """Per-batch constants of the sync-free forward: node counts, the bond edges as a CSR by target atom, capacities of
+        the per-step edge buffers (upper bounds that hold for ANY pose), int32 views.  One host read per batch."""
+        rec, lig, ll = data['receptor'], data['ligand'], data['ligand', 'ligand']
+        B, dev = data.num_graphs, lig.pos.device
+        i32 = lambda t: t.to(torch.int32).contiguous()
+        n_lig, n_rec = lig.batch.shape[0], rec.batch.shape[0]
+        lig_cnt = (c['lig_ptr'][1:] - c['lig_ptr'][:-1])
+        rec_cnt = (c['rec_ptr'][1:] - c['rec_ptr'][:-1])
+        host = torch.stack([lig_cnt, rec_cnt]).cpu()                       # the one host read of the batch
+        c['lig_cnt_f'] = lig_cnt.float().unsqueeze(1)
+        c['rec_max'] = int(host[1].max()) if B else 0
+        c['cap_cross'] = int((host[0].long() * host[1].long()).sum())      # every ligand atom x every residue of its complex
+        c['lig_batch32'], c['rec_batch32'] = i32(lig.batch), i32(rec.batch)
+        c['rr_gid32'] = i32(c['rr_tgt_batch'])
+        # bond edges grouped by their convolution target (edge_index[0]), original order kept inside a group
+        ei = ll.edge_index.long()
+        order = torch.sort(ei[0], stable=True).indices
+        c['pre_col'] = i32(ei[1][order])
+        cnt = torch.bincount(ei[0], minlength=n_lig)[:n_lig] if ei.shape[1] else torch.zeros(n_lig, dtype=torch.long, device=dev)
+        ptr = torch.zeros(n_lig + 1, dtype=torch.int32, device=dev)
+        ptr[1:] = torch.cumsum(cnt, 0)
+        c['pre_ptr'], c['pre_cnt'] = ptr, i32(cnt)
+        attr = ll.edge_attr.float()[order] if ei.shape[1] else torch.zeros((0, self.in_lig_edge_features), device=dev)
+        c['pre_attr'] = torch.cat([attr, torch.zeros((1, attr.shape[1]), device=dev)], 0)     # row -1: "not a bond"
+        c['cap_ll'] = int(ei.shape[1]) + 32 * n_lig
+        c['bond_lig_batch'] = lig.batch[c['bonds'][0]] if c['n_bonds'] else None
+        c['cap_tor'] = 32 * c['n_bonds']
+        c['bond_batch32'] = i32(c['bond_batch']) if c['n_bonds'] else None
 
     def _ligand_graph(self, data, c):
         """Bond edges + radius graph, sorted by convolution target (models/cg_model.py:467-497)."""
@@ -259,6 +291,17 @@ class CGModel(nn.Module):
         return li, ri, edge_attr, vec, self.get_edge_weight(vec, cutoff_d)
 
     # ---------------------------------------------------------------------------------------------------------
+    def sync_free_capable(self):
+        """The forward can run without any host synchronisation (and so inside a CUDA graph) when every convolution of the
+        stack has a shape the fully fused kernel supports; otherwise the neighbour-list sizes go through the host."""
+        if self._sync_free is None:
+            ok = os.environ.get('DDB200_SYNC_FREE', '1') != '0'
+            ok = ok and self.embed_also_ligand
+            for layer in list(self.conv_layers) + list(getattr(self, 'lig_emb_layers', [])):
+                ok = ok and layer.fused_capable(self.ns, self.ns)
+            self._sync_free = bool(ok)
+        return self._sync_free
+
     @torch.no_grad()
     def forward(self, data):
         if self.training:
@@ -268,9 +311,118 @@ class CGModel(nn.Module):
             raise RuntimeError("diffdock_b200.CGModel runs on CUDA tensors only (no CPU fallback): data.to('cuda')")
         if self.no_aminoacid_identities:
             rec.x = rec.x * 0
+        c = self._static(data)
+        if self.sync_free_capable() and c['rec_max'] <= 10000:      # cap of the cross graph (models/cg_model.py:546) not binding
+            return self._forward_sync_free(data, c)
+        return self._forward_host_sized(data, c)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _forward_sync_free(self, data, c):
+        """The whole forward without a device->host read: every per-step neighbour list is written into an upper-bound
+        buffer by ddb200_graph_fill with its live length kept in device memory, the reverse direction of the cross graph is
+        an index permutation of the forward one, the ligand-receptor edge embedding is one kernel, and the convolutions
+        take (capacity, device count).  Shapes are static for a given batch, so a reverse-diffusion step can be captured in
+        a CUDA graph (diffdock_b200/sampling.py)."""
+        lig, rec = data['ligand'], data['receptor']
+        ns, B = self.ns, data.num_graphs
+        dev = lig.pos.device
+        tr_sigma, rot_sigma, tor_sigma = self.t_to_sigma(*[data.complex_t[k] for k in ('tr', 'rot', 'tor')])
+        n_lig, n_rec = lig.batch.shape[0], rec.batch.shape[0]
+        pos, rpos = lig.pos.float().contiguous(), rec.pos.float().contiguous()
+        scan = lambda cnt: torch.cumsum(cnt, 0, dtype=torch.int32)
+
+        # -- embeddings (models/cg_model.py:272-306) --------------------------------------------------------------
+        sig = self.rec_sigma_embedding(self.timestep_emb_func(data.complex_t['tr'])).contiguous()      # [B, ns]
+        rec_node = rec.rec_node_attr.clone()
+        rec_node[:, :ns] += sig[rec.batch]
+        lig.node_sigma_emb = self.timestep_emb_func(lig.node_t['tr'])
+
+        # -- ligand graph: bonds + radius graph, CSR by target, built on the device (:467-497) -------------------------
+        cnt = ops.radius_count(pos, pos, c['lig_ptr'], c['lig_batch32'], r=self.lig_max_radius, max_num_neighbors=33,
+                               exclude_self=True) + c['pre_cnt']
+        incl = scan(cnt)
+        ll_n = incl[-1:]
+        ll_tgt, ll_src, ll_vec, ll_eid, _ = ops.graph_fill(
+            pos, pos, c['lig_ptr'], c['lig_batch32'], (incl - cnt).contiguous(), c['cap_ll'], r=self.lig_max_radius,
+            max_num_neighbors=33, exclude_self=True, pre_ptr=c['pre_ptr'], pre_col=c['pre_col'], want_eid=True, fill_row=0)
+        tgt_l = ll_tgt.long()
+        ll_attr = torch.cat([c['pre_attr'][ll_eid.long()], lig.node_sigma_emb[tgt_l],
+                             self.lig_distance_expansion(ll_vec.norm(dim=-1))], 1)
+        ll_ea = self.lig_edge_embedding(ll_attr)
+        ll_ew = self.get_edge_weight(ll_vec, self.lig_max_radius)
+        lig_node = self.lig_node_embedding(torch.cat([lig.x.float(), lig.node_sigma_emb], 1))
+        ewt = lambda w: w.reshape(-1).contiguous() if torch.is_tensor(w) else None
+        g_ll = (ll_tgt, ll_src, ll_ea, ll_vec, ewt(ll_ew), dict(n_edges_dev=ll_n))
+        for layer in self.lig_emb_layers:
+            lig_node = layer.forward_groups(lig_node, [g_ll], gather_scalars=ns)
+
+        # -- cross graph, both directions (:321-327, :539-562) ------------------------------------------------------------
+        if self.dynamic_max_cross:
+            rpg, r_cross = (tr_sigma * 3 + 20).reshape(-1).float().contiguous(), 1.0
+        else:
+            rpg, r_cross = None, float(self.cross_max_distance)
+        cap = c['cap_cross']
+        cnt = ops.radius_count(rpos, pos, c['rec_ptr'], c['lig_batch32'], r=r_cross, r_per_graph=rpg, max_num_neighbors=10000)
+        incl = scan(cnt)
+        lr_n = incl[-1:]
+        slot = torch.empty((n_lig, max(c['rec_max'], 1)), dtype=torch.int32, device=dev)
+        smooth = self.smooth_edges
+        lr_tgt, lr_src, lr_vec, _, _ = ops.graph_fill(
+            rpos, pos, c['rec_ptr'], c['lig_batch32'], (incl - cnt).contiguous(), cap, r=r_cross, r_per_graph=rpg,
+            max_num_neighbors=10000, slot_out=slot, slot_ld=slot.shape[1], col_offset=n_lig, fill_row=0 if smooth else None)
+        cnt_r = ops.radius_count(pos, rpos, c['lig_ptr'], c['rec_batch32'], r=r_cross, r_per_graph=rpg,
+                                 max_num_neighbors=1 << 30)
+        incl_r = scan(cnt_r)
+        rl_tgt, rl_src, _, _, rl_perm = ops.graph_fill(
+            pos, rpos, c['lig_ptr'], c['rec_batch32'], (incl_r - cnt_r).contiguous(), cap, r=r_cross, r_per_graph=rpg,
+            max_num_neighbors=1 << 30, want_vec=False, slot_in=slot, y_ptr=c['rec_ptr'], slot_ld=slot.shape[1],
+            want_perm=True, row_offset=n_lig)
+        lr_ea = self._cross_edge_embedding(lig.node_sigma_emb, lr_vec, lr_tgt, lr_n)
+        lr_ew = None
+        if smooth:
+            cutoff_d = rpg[lig.batch[lr_tgt.long()]] if rpg is not None else r_cross
+            lr_ew = ewt(self.get_edge_weight(lr_vec, cutoff_d))
+
+        # -- joint graph: four edge groups (:329-338) ---------------------------------------------------------------
+        node = torch.cat([lig_node, rec_node], 0)
+        rr_tgt32 = c.setdefault('rr_tgt32', {}).get(n_lig)
+        if rr_tgt32 is None:
+            i32 = lambda t: t.to(torch.int32).contiguous()
+            rr_tgt32 = c['rr_tgt32'][n_lig] = (i32(c['rr_tgt'] + n_lig), i32(c['rr_src'] + n_lig))
+        groups = [
+            g_ll,                                                                                         # lig <- lig
+            (lr_tgt, lr_src, lr_ea, lr_vec, lr_ew, dict(n_edges_dev=lr_n)),                               # lig <- rec
+            (rr_tgt32[0], rr_tgt32[1], c['rr_ea'], c['rr_vec'], ewt(c['rr_ew']),
+             dict(ea_add=sig, ea_add_idx=c['rr_gid32'])),                                                 # rec <- rec
+            (rl_tgt, rl_src, lr_ea, lr_vec, lr_ew, dict(n_edges_dev=lr_n, edge_perm=rl_perm, vec_sign=-1.0)),   # rec <- lig
+        ]
+        L = len(self.conv_layers)
+        for l, layer in enumerate(self.conv_layers):
+            use = groups if l < L - 1 else groups[:2]       # last layer: only edges that end on ligand atoms (:347-349)
+            node = layer.forward_groups(node, use, gather_scalars=ns)
+        lig_node = node[:n_lig]
+        return self._heads(data, c, lig_node, tr_sigma, rot_sigma, tor_sigma, sync_free=True)
+
+    def _cross_edge_embedding(self, node_sigma_emb, vec, row, n_dev):
+        """cross_edge_embedding(cat[sigma_emb[lig], RBF(d)]) (models/cg_model.py:326,553-554): the sigma half of the first
+        Linear is applied per ligand NODE, the rest per edge in one kernel (ddb200_edge_embed)."""
+        l1, l2 = self.cross_edge_embedding[0], self.cross_edge_embedding[-1]
+        S = node_sigma_emb.shape[1]
+        gs = self.cross_distance_expansion
+        if (gs.offset.shape[0], self.ns) in ops.EDGE_EMBED_SHAPES and len(self.cross_edge_embedding) == 4:
+            u = torch.addmm(l1.bias, node_sigma_emb, l1.weight[:, :S].t()).contiguous()
+            return ops.edge_embed(vec, row, u, l1.weight[:, S:].contiguous(), l2.weight.contiguous(), l2.bias.contiguous(),
+                                  gs.offset.contiguous(), float(gs.coeff), n_dev)
+        attr = torch.cat([node_sigma_emb[row.long()], gs(vec.norm(dim=-1))], 1)      # library path on the padded buffer
+        return self.cross_edge_embedding(attr)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _forward_host_sized(self, data, c):
+        """Forward with exactly-sized neighbour lists (one host read of each edge count): convolution shapes outside the
+        fused kernel's templates, or more than 10000 residues per complex."""
+        lig, rec = data['ligand'], data['receptor']
         ns, B = self.ns, data.num_graphs
         tr_sigma, rot_sigma, tor_sigma = self.t_to_sigma(*[data.complex_t[k] for k in ('tr', 'rot', 'tor')])
-        c = self._static(data)
 
         # -- embeddings (models/cg_model.py:272-306) --------------------------------------------------------------
         sig = self.rec_sigma_embedding(self.timestep_emb_func(data.complex_t['tr']))
@@ -314,12 +466,17 @@ class CGModel(nn.Module):
                 use = [tuple(torch.cat([g[k] for g in use]) if use[0][k] is not None else None for k in range(5))]
             node = layer.forward_groups(node, use, gather_scalars=ns)
         lig_node = node[:n_lig]
+        return self._heads(data, c, lig_node, tr_sigma, rot_sigma, tor_sigma, sync_free=False)
 
+    def _heads(self, data, c, lig_node, tr_sigma, rot_sigma, tor_sigma, sync_free):
+        lig = data['ligand']
+        ns, B = self.ns, data.num_graphs
+        n_lig = lig_node.shape[0]
         # -- translation / rotation head (:368-395) -----------------------------------------------------------------
         pos = lig.pos.float()
         arange = torch.arange(n_lig, device=pos.device)
         center = torch.zeros((B, 3), device=pos.device).index_add_(0, lig.batch, pos)
-        center = center / torch.bincount(lig.batch, minlength=B).unsqueeze(1)
+        center = center / c['lig_cnt_f']
         c_vec = pos - center[lig.batch]
         c_ea = torch.cat([self.center_distance_expansion(c_vec.norm(dim=-1)), lig.node_sigma_emb], 1)
         c_ea = self.center_edge_embedding(c_ea)
@@ -343,19 +500,33 @@ class CGModel(nn.Module):
 
         # -- torsion head (:406-423) --------------------------------------------------------------------------------
         bonds = c['bonds']
-        bond_pos = (pos[bonds[0]] + pos[bonds[1]]) / 2
-        bi, ai, _ = ops.radius(pos, bond_pos, c['lig_ptr'], c['bond_batch'], r=self.lig_max_radius, max_num_neighbors=32)
-        bi, ai = bi.long(), ai.long()
-        t_vec = pos[ai] - bond_pos[bi]
+        n_bonds = c['n_bonds']
+        bond_pos = ((pos[bonds[0]] + pos[bonds[1]]) / 2).contiguous()
+        if sync_free:
+            # upper-bound buffer (32 atoms per bond, models/cg_model.py:630); slots beyond the live count point at an extra
+            # dummy bond row (index n_bonds) that is dropped after the convolution
+            pos_c = pos.contiguous()
+            cnt = ops.radius_count(pos_c, bond_pos, c['lig_ptr'], c['bond_batch32'], r=self.lig_max_radius, max_num_neighbors=32)
+            incl = torch.cumsum(cnt, 0, dtype=torch.int32)
+            bi32, ai32, t_vec, _, _ = ops.graph_fill(pos_c, bond_pos, c['lig_ptr'], c['bond_batch32'], (incl - cnt).contiguous(),
+                                                     c['cap_tor'], r=self.lig_max_radius, max_num_neighbors=32, fill_row=n_bonds)
+            bi, ai = bi32.long(), ai32.long()
+            bi_g = bi.clamp_max(n_bonds - 1)            # gathers of per-bond quantities for the dummy slots: any valid row
+            n_out = n_bonds + 1
+        else:
+            bi, ai, _ = ops.radius(pos, bond_pos, c['lig_ptr'], c['bond_batch'], r=self.lig_max_radius, max_num_neighbors=32)
+            bi, ai = bi.long(), ai.long()
+            t_vec = pos[ai] - bond_pos[bi]
+            bi_g, n_out = bi, n_bonds
         t_ea = self.final_edge_embedding(self.lig_distance_expansion(t_vec.norm(dim=-1)))
         bond_vec = pos[bonds[1]] - pos[bonds[0]]
         bond_attr = lig_node[bonds[0]] + lig_node[bonds[1]]
-        t_sh = torch.einsum('ea,eb,abc->ec', _sh_full(t_vec, self.sh_lmax), _sh_l2(bond_vec)[bi], self._tor_tp)
-        t_ea = torch.cat([t_ea, lig_node[ai, :ns], bond_attr[bi, :ns]], -1)
-        tor_pred = self.tor_bond_conv(lig_node, torch.stack([bi, ai]), t_ea, t_sh, out_nodes=c['n_bonds'], reduce='mean',
+        t_sh = torch.einsum('ea,eb,abc->ec', _sh_full(t_vec, self.sh_lmax), _sh_l2(bond_vec)[bi_g], self._tor_tp)
+        t_ea = torch.cat([t_ea, lig_node[ai, :ns], bond_attr[bi_g, :ns]], -1)
+        tor_pred = self.tor_bond_conv(lig_node, torch.stack([bi, ai]), t_ea, t_sh, out_nodes=n_out, reduce='mean',
                                       edge_weight=self.get_edge_weight(t_vec, self.lig_max_radius), assume_sorted=True)
-        tor_pred = self.tor_final_layer(tor_pred).squeeze(1)
-        edge_sigma = tor_sigma[lig.batch][data['ligand', 'ligand'].edge_index[0]][lig.edge_mask]
+        tor_pred = self.tor_final_layer(tor_pred[:n_bonds]).squeeze(1)
+        edge_sigma = tor_sigma[c['bond_lig_batch']]
         if self.scale_by_sigma:
             tor_pred = tor_pred * torch.sqrt(self._torus_score_norm(edge_sigma))
         return tr_pred, rot_pred, tor_pred, None

@@ -3,16 +3,26 @@
 //
 //   for a unit of 256 CSR-sorted edges (a CTA pair on tcgen05 cta_group::2, 128 edges = 128 TMEM lanes per CTA, persistent
 //   over units; CG = 1: one CTA per 128-edge tile):
-//     A0' = split-bf16([edge_attr | node[tgt,:ns] | node[src,:ns] | 1 1])      built in shared memory (128B swizzle)
-//     H   = relu(A0' x W1'^T)          tcgen05.mma -> TMEM -> registers -> A' image (bias folded via the ones columns)
+//     A0' = split-bf16([edge_attr (+ per-graph term) | node[tgt,:ns] | node[src,:ns]])   built in shared memory (128B swizzle)
+//     H   = relu(A0' x W1'^T)          tcgen05.mma -> TMEM -> registers -> A' image (bias folded via two constant-one columns)
 //     for every N tile (whole rows u of one path block [mul_in, mul_out], <= 192 columns):
 //        Wt = A' x W2'^T[tile]         tcgen05.mma into one of two TMEM accumulators   (B' images streamed by TMA bulk copies)
 //        consumer thread e (= TMEM lane): acc[w,k] += Wt[e, (u,w)] * z_e[u,k],   z_e[u,k] = sum_i x[src_e][u,i] M_e[i,k],
 //                                         M_e = edge_weight * coef * C . Y(vec_e)       (tcgen05.ld 32x32b.x32 + FFMA)
-//     at the end of an output irrep: sum[tgt_e, irrep] += acc  (segmented warp reduction over runs of equal targets)
+//     at the end of an output irrep: sum[tgt_e, irrep] += acc  (run reduction over equal targets through shared memory, then
+//                                                              one coalesced RED.ADD per run and 32 output values)
+//
+// Operand layout: BOTH operand images hold each split part once - activation [hi | lo | 1 1 0..], static operand
+// [hi | lo | b_hi b_lo 0..] (2 Kp + 16 columns, Kp = K rounded up to 16).  The three products hi.hi + hi.lo + lo.hi (+ bias)
+// are formed by an MMA schedule over 16-column steps: a `hi` step of B is multiplied with the hi AND the lo columns of A (two
+// MMAs on one staged block), a `lo` step with the hi columns, the bias step with the constant-one columns.  Compared with
+// concatenating [hi | hi | lo] x [hi | lo | hi] along K this stages 5 instead of 7 k-blocks of B per tile (the kernel is
+// bound by the latency of that stream: same ring, 40 % more tensor work per staged byte), frees 32 KB of shared memory on
+// the A side and a third of the activation stores.
 //
 // Replaces models/tensor_layers.py:139-144 / :204-221 *including* the FCBlock at :140/:211 and the edge_attr_ assembly of
-// models/cg_model.py:342-349.  Plan (tiles, operand images, CG terms) is built by diffdock_b200/fused.py.
+// models/cg_model.py:342-349 (and the per-call sigma-embedding add of :298-301 through `ea_add`).
+// Plan (tiles, operand images, dense Clebsch-Gordan tables) is built by diffdock_b200/fused.py.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,11 +39,15 @@ constexpr int B_IMAGE_BYTES = BN * BK * 2;       // 32 KB: one k-block image of 
 // rows of every B image (half the L2->smem traffic and half the B reads per SM), so the ring can be deeper.
 constexpr int MAX_N = 192;                       // widest N tile of a plan (and widest hidden layer)
 template <int CG> struct Ring {
-  static constexpr int STAGES = 4 * CG;
+  static constexpr int STAGES = CG == 2 ? 9 : 4;
   static constexpr int STAGE_BYTES = MAX_N * BK * 2 / CG;     // 24 KB, or 12 KB per CTA of a pair
 };
-constexpr int MAX_KB = 7;                        // K' <= 448 (K <= 149)
+constexpr int MAX_KB = 5;                        // k-blocks of either operand image: 2 Kp + 16 <= 320  (Kp <= 144)
+constexpr int MAX_KA = MAX_KB;
+constexpr int OPS_PER_KB = 8;                    // MMAs that read one staged k-block of B (4 steps x up to 2 A partners)
 constexpr int THREADS = 256;
+constexpr int MAX_TILES = 160, MAX_PATHS = 16, MTAB = 48;     // per path: dense [3][3][5] table, padded to 48 floats
+constexpr int FLUSH_LD = 33;                     // padded row of the per-warp scatter staging buffer [48][33]
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -83,9 +97,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
-// Pair kernel: barriers that are signalled from the other SM (remote arrive, multicast commit) are polled with test_wait
-// (measured: try_wait's suspended wait adds microseconds per hand-off when the completing arrival comes from a peer CTA)
 // same, without the cluster-scope release: for forwarding a completion the thread itself wrote nothing for
+// (cluster-scope release/acquire on mbarrier operations costs ~1000 clocks each, measured)
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
@@ -114,8 +127,6 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-template <int CG>
-__device__ __forceinline__ void mbar_wait_cg(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 template <int CG>
@@ -167,13 +178,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void put_a(unsigned char* sA, int r, int col, __nv_bfloat16 v) {
   const int kb = col >> 6, c = (col & 63) >> 3, j = col & 7;
   *reinterpret_cast<__nv_bfloat16*>(sA + (size_t)kb * A_KB_BYTES + r * 128 + ((c ^ (r & 7)) << 4) + j * 2) = v;
 }
-
 // 8 consecutive columns col0..col0+7 (col0 % 8 == 0) of row r = one 16-byte chunk of the swizzled image
 __device__ __forceinline__ void put_a8(unsigned char* sA, int r, int col0, const uint4& v) {
   const int kb = col0 >> 6, c = (col0 & 63) >> 3;
@@ -193,45 +203,58 @@ __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+// The tail of an operand image row: zero the padding of the hi / lo sections (K..Kp), write the two constant-one columns
+// that carry the folded bias and zero the rest of their 16-column step.
+__device__ __forceinline__ void put_a_tail(unsigned char* sA, int r, int K, int Kp) {
+  const __nv_bfloat16 one = __float2bfloat16(1.0f), zero = __float2bfloat16(0.f);
+  for (int c = K; c < Kp; ++c) { put_a(sA, r, c, zero); put_a(sA, r, Kp + c, zero); }
+  const uint32_t ones = 0x3F803F80u;     // two bf16 1.0
+  put_a8(sA, r, 2 * Kp, make_uint4(ones, 0u, 0u, 0u));
+  put_a8(sA, r, 2 * Kp + 8, make_uint4(0u, 0u, 0u, 0u));
+  (void)one;
+}
 
 struct FusedParams {
   const float* ea; long long ld_ea; int ne;          // per-edge attributes
   const float* node; long long ld_node; int ns;      // node scalars for the radial MLP (both end points)
   const int* tgt; const int* src;                    // scatter target / gathered node of every edge
-  const __nv_bfloat16* w1img; int K1, n_kb1, H, n_kb;
+  const int* perm;                                   // optional: row of ea / vec / ew that belongs to edge e
+  const float* ea_add; const int* ea_add_idx;        // optional: ea row += ea_add[ea_add_idx[e], :ne]
+  float vec_sign;
+  const __nv_bfloat16* w1img; int K1, K1p, n_kb1, H, Hp, n_kb;
   const __nv_bfloat16* w2img;                        // [n_tiles][n_kb][256][64]
-  const int* tiles; int n_tiles;                     // [n_tiles][8]: kind, N_mma, x_off, rows, d_in, out_off, flags, ment_off
-  const int* ment; const int* term_y; const float* term_v; int n_ment, n_terms;
-  const float* x; long long ld_x;                    // node irreps gathered by src
+  const int* tiles; int n_tiles;                     // [n_tiles][8]: kind, N_mma, x_off, rows, d_in, out_off, flags | sh_off << 8, path
+  const float* mtab; int n_paths;                    // [n_paths][48]: coef * C[i, j, k] as [i][k][j], i,k < 3, j < 5
+  const float* x; long long ld_x; int x_vec2;        // node irreps gathered by src
   const float* vec; const float* ew; int lmax;
   float* sum; int d_out; float* cnt;
-  long long n_edges;
-  int seg_flush;                                     // segmented-shuffle scatter (1) or one atomic per lane and value (0)
+  long long n_edges; const int* n_edges_dev;
   int dbg_noload;                                    // diagnostics: skip the B copies (timing only, results garbage)
-  unsigned long long* dbg;                           // optional [16] clock counters (DDB200_FUSED_DEBUG=1), else nullptr
+  unsigned long long* dbg;                           // optional [32] clock counters (DDB200_FUSED_DEBUG=1), else nullptr
 };
 
 // clock counters of the warp roles: compiled in only for the DBG instantiation (DDB200_FUSED_DEBUG=1)
 #define DBG_T() (DBG ? clock64() : 0ll)
 #define DBG_ADD(i, v) do { if (DBG) atomicAdd(p.dbg + (i), (unsigned long long)(v)); } while (0)
 
-constexpr int MAX_TILES = 160, MAX_MENT = 256, MAX_TERMS = 512;
-
 // ---- consumer: one TMEM accumulator tile (ROWS rows u of a [mul_in, MULOUT] block) times z -> acc -------------------------
+// Only the first `nch` 32-column chunks hold MMA results (the last tile of a path block may be narrower than the full tile).
 template <int MULOUT, int DOUT, int ROWS>
-__device__ __forceinline__ void consume_tile(uint32_t taddr, const float* __restrict__ z, float* __restrict__ acc) {
+__device__ __forceinline__ void consume_tile(uint32_t taddr, int nch, const float* __restrict__ z, float* __restrict__ acc) {
   constexpr int NCOL = MULOUT * ROWS;
   static_assert(NCOL % 32 == 0 && NCOL <= MAX_N, "tile width");
 #pragma unroll
   for (int c = 0; c < NCOL / 32; ++c) {
-    uint32_t v[32];
-    tmem_ld32(taddr + c * 32, v);
+    if (c < nch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c * 32, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j, row = col / MULOUT, w = col % MULOUT;     // compile-time after unrolling
-      const float wv = __uint_as_float(v[j]);
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j, row = col / MULOUT, w = col % MULOUT;     // compile-time after unrolling
+        const float wv = __uint_as_float(v[j]);
 #pragma unroll
-      for (int k = 0; k < DOUT; ++k) acc[w * DOUT + k] = fmaf(wv, z[row * DOUT + k], acc[w * DOUT + k]);
+        for (int k = 0; k < DOUT; ++k) acc[w * DOUT + k] = fmaf(wv, z[row * DOUT + k], acc[w * DOUT + k]);
+      }
     }
   }
 }
@@ -253,31 +276,60 @@ __device__ __forceinline__ void make_z(const float* __restrict__ xv, const float
 }
 
 constexpr int XN = 48;     // gathered node values of one tile: at most 16 rows x 3 components
-__device__ __forceinline__ void prefetch_x(const float* __restrict__ src, int cnt, float* __restrict__ xn) {
+__device__ __forceinline__ void prefetch_x(const float* __restrict__ src, int cnt, int vec2, float* __restrict__ xn) {
+  if (vec2) {          // 8-byte loads: every tile offset and count of the plan is even
 #pragma unroll
-  for (int j = 0; j < XN; ++j) xn[j] = (j < cnt) ? __ldg(src + j) : 0.f;
+    for (int j = 0; j < XN / 2; ++j) {
+      float2 v = make_float2(0.f, 0.f);
+      if (2 * j < cnt) v = __ldg(reinterpret_cast<const float2*>(src) + j);
+      xn[2 * j] = v.x; xn[2 * j + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < XN; ++j) xn[j] = (j < cnt) ? __ldg(src + j) : 0.f;
+  }
 }
 
 // z is formed from the node values prefetched during the previous tile, then the NEXT tile's values are requested, all
 // before waiting for the accumulator: the gather latency overlaps this tile's contraction
-template <int CG, int MULOUT, int DOUT, int ROWS>
-__device__ __forceinline__ void tile_body(uint32_t taddr, float* xn, int d_in, const float* M, float* acc,
-                                          const float* xnext, int cnt_next, uint64_t* tfull_bar, uint32_t parity,
+template <int MULOUT, int DOUT, int ROWS>
+__device__ __forceinline__ void tile_body(uint32_t taddr, int nch, float* xn, int d_in, const float* M, float* acc,
+                                          const float* xnext, int cnt_next, int vec2, uint64_t* tfull_bar, uint32_t parity,
                                           unsigned long long* dbg) {
   float z[ROWS * DOUT];
   const long long t0 = dbg ? clock64() : 0ll;
   if (d_in == 1) make_z<1, DOUT, ROWS>(xn, M, z);
   else make_z<3, DOUT, ROWS>(xn, M, z);
-  prefetch_x(xnext, cnt_next, xn);
+  prefetch_x(xnext, cnt_next, vec2, xn);
   const long long t1 = dbg ? clock64() : 0ll;
-  mbar_wait_cg<CG>(tfull_bar, parity);
+  mbar_wait(tfull_bar, parity);
   tc_fence_after();
   const long long t2 = dbg ? clock64() : 0ll;
-  consume_tile<MULOUT, DOUT, ROWS>(taddr, z, acc);
+  consume_tile<MULOUT, DOUT, ROWS>(taddr, nch, z, acc);
   if (dbg) {
     atomicAdd(dbg + 22, (unsigned long long)(t1 - t0));
     atomicAdd(dbg + 23, (unsigned long long)(t2 - t1));
     atomicAdd(dbg + 24, (unsigned long long)(clock64() - t2));
+  }
+}
+
+// MMA schedule of one staged k-block of B (4 steps of 16 columns; images [hi | lo | bias], S = Kp / 16 steps per part):
+// step c < S (hi): x A hi (column block c) and x A lo (block S + c);  S <= c < 2S (lo): x A hi (block c - S);
+// c == 2S (bias): x A ones (block 2S).  An op word = A descriptor offset (16-byte units) | B step within the k-block << 28;
+// 0xFFFFFFFF terminates the list.
+__device__ __forceinline__ uint32_t a_block_offset(int c) { return (uint32_t)((c >> 2) * (A_KB_BYTES >> 4) + (c & 3) * 2); }
+__device__ __forceinline__ void build_ops(uint32_t* ops, int S) {     // ops[MAX_KB][OPS_PER_KB]
+  for (int kb = 0; kb < MAX_KB; ++kb) {
+    int n = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int c = kb * 4 + j;
+      if (c < S) {
+        ops[kb * OPS_PER_KB + n++] = a_block_offset(c) | ((uint32_t)j << 28);
+        ops[kb * OPS_PER_KB + n++] = a_block_offset(S + c) | ((uint32_t)j << 28);
+      } else if (c < 2 * S) ops[kb * OPS_PER_KB + n++] = a_block_offset(c - S) | ((uint32_t)j << 28);
+      else if (c == 2 * S) ops[kb * OPS_PER_KB + n++] = a_block_offset(2 * S) | ((uint32_t)j << 28);
+    }
+    for (; n < OPS_PER_KB; ++n) ops[kb * OPS_PER_KB + n] = 0xFFFFFFFFu;
   }
 }
 
@@ -286,15 +338,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
   constexpr int STAGES = Ring<CG>::STAGES, B_STAGE_BYTES = Ring<CG>::STAGE_BYTES;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int n_kb_max = p.n_kb > p.n_kb1 ? p.n_kb : p.n_kb1;
-  unsigned char* sA = smem;                                      // n_kb_max x 16 KB
-  unsigned char* sB = smem + (size_t)n_kb_max * A_KB_BYTES;      // ring of B stages
+  unsigned char* sA = smem;                                      // MAX_KA x 16 KB
+  unsigned char* sB = smem + (size_t)MAX_KA * A_KB_BYTES;        // ring of B stages
   float* sY = reinterpret_cast<float*>(sB + STAGES * B_STAGE_BYTES);   // [9][128] spherical harmonics per consumer thread
-  int* sTiles = reinterpret_cast<int*>(sY + 9 * 128);            // [MAX_TILES][8]
-  int* sMent = sTiles + MAX_TILES * 8;                           // [MAX_MENT][2]
-  int* sTermY = sMent + MAX_MENT * 2;                            // [MAX_TERMS]
-  float* sTermV = reinterpret_cast<float*>(sTermY + MAX_TERMS);  // [MAX_TERMS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sTermV + MAX_TERMS);
+  float* sFlush = sY + 9 * 128;                                  // [4 warps][48][33] scatter staging
+  float* sMtab = sFlush + 4 * 48 * FLUSH_LD;                     // [MAX_PATHS][48]
+  int* sTiles = reinterpret_cast<int*>(sMtab + MAX_PATHS * MTAB);   // [MAX_TILES][8]
+  uint32_t* sOps = reinterpret_cast<uint32_t*>(sTiles + MAX_TILES * 8);   // [2][MAX_KB][OPS_PER_KB] MMA schedules (16 B aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOps + 2 * MAX_KB * OPS_PER_KB);
   uint64_t* full = bars;                 // this CTA's part of B stage s has landed (TMA complete_tx)
   uint64_t* empty = bars + STAGES;       // the MMAs reading stage s are done (commit; both CTAs of a pair)
   uint64_t* pfull = bars + 2 * STAGES;   // leader only: the peer's part of stage s has landed (relayed by the peer)
@@ -306,9 +357,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
+  const int S1 = p.K1p >> 4, S2 = p.Hp >> 4;
   for (int i = tid; i < p.n_tiles * 8; i += THREADS) sTiles[i] = p.tiles[i];
-  for (int i = tid; i < p.n_ment * 2; i += THREADS) sMent[i] = p.ment[i];
-  for (int i = tid; i < p.n_terms; i += THREADS) { sTermY[i] = p.term_y[i]; sTermV[i] = p.term_v[i]; }
+  for (int i = tid; i < p.n_paths * MTAB; i += THREADS) sMtab[i] = p.mtab[i];
+  if (tid == 32) build_ops(sOps, S1);
+  if (tid == 64) build_ops(sOps + MAX_KB * OPS_PER_KB, S2);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&pfull[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * CG); }
@@ -334,76 +387,97 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
   const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((BM * CG) >> 4) << 24);
   const int n1 = ((p.H + 15) / 16) * 16;
 
-  const long long n_mtiles = (p.n_edges + BM - 1) / BM;
+  // the edge count may live on the device (neighbour lists built without a host round trip): p.n_edges is then its bound
+  long long n_edges = p.n_edges;
+  if (p.n_edges_dev) { const long long nd = __ldg(p.n_edges_dev); n_edges = nd < n_edges ? (nd < 0 ? 0 : nd) : n_edges; }
+  const long long n_mtiles = (n_edges + BM - 1) / BM;
   const long long n_units = (n_mtiles + CG - 1) / CG;       // a unit = the CG edge tiles one MMA covers
   uint32_t pc = 0, mc = 0, ma = 0, ea = 0, mtc = 0, rc = 0;
-  const __nv_bfloat16 one = __float2bfloat16(1.0f), zero = __float2bfloat16(0.f);
 
   for (long long unit = blockIdx.x / CG; unit < n_units; unit += gridDim.x / CG) {
     const long long mt = unit * CG + rank;                   // may be one past the end for the peer: all rows invalid
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     const long long t_unit = DBG_T();
-    // ---- A0' image: [hi | hi | lo | 1 1 | 0..] of [edge_attr | node[tgt,:ns] | node[src,:ns]] -----------------------
+    // ---- A0' image: [hi | lo | 1 1 0..] of [edge_attr (+ per-graph term) | node[tgt,:ns] | node[src,:ns]] -------------
     {
       const long long e0 = mt * BM;
-      const int Kin = p.K1, kpad = p.n_kb1 * BK;
-      for (int idx = tid; idx < BM * (kpad - 3 * Kin); idx += THREADS) {
-        const int r = idx / (kpad - 3 * Kin), off = idx % (kpad - 3 * Kin);
-        put_a(sA, r, 3 * Kin + off, off < 2 ? one : zero);
-      }
+      const int Kin = p.K1, Kp = p.K1p;
+      if (tid < BM) put_a_tail(sA, tid, Kin, Kp);
       if (((p.ne | p.ns) & 7) == 0 && ((p.ld_ea | p.ld_node) & 3) == 0) {
-        // vector path: one work item = 8 consecutive input columns of one edge = two independent 16-byte loads, three
-        // 16-byte shared stores; all of a thread's loads are issued before the first conversion
+        // vector path: one work item = 8 consecutive input columns of one edge = two independent 16-byte loads, two
+        // 16-byte shared stores; the index loads of all of a thread's items are issued first, then all data loads, then
+        // the conversions (one pass for K = 144: 2304 items / 256 threads = 9)
         const int groups = Kin >> 3, items = BM * groups;
-        constexpr int PER = 4;
+        constexpr int PER = 9;
         for (int base = tid; base < items; base += THREADS * PER) {
           float4 f[PER][2];
-          int rr[PER], gg[PER];
+          long long off[PER];
+          int rr[PER], gg[PER], ai[PER];
+          const float* bp[PER];
 #pragma unroll
           for (int u = 0; u < PER; ++u) {
             const int idx = base + u * THREADS;
-            f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rr[u] = -1;
+            rr[u] = -1; ai[u] = -1; off[u] = 0; bp[u] = nullptr;
             if (idx < items) {
               const int r = idx / groups, g = idx - r * groups, k = g << 3;
-              rr[u] = r; gg[u] = g;
               const long long e = e0 + r;
-              if (e < p.n_edges) {
-                const float* srcp;
-                if (k < p.ne) srcp = p.ea + e * p.ld_ea + k;
-                else if (k < p.ne + p.ns) srcp = p.node + (long long)__ldg(p.tgt + e) * p.ld_node + (k - p.ne);
-                else srcp = p.node + (long long)__ldg(p.src + e) * p.ld_node + (k - p.ne - p.ns);
-                f[u][0] = __ldg(reinterpret_cast<const float4*>(srcp));
-                f[u][1] = __ldg(reinterpret_cast<const float4*>(srcp) + 1);
-              }
+              if (e < n_edges) {
+                rr[u] = r; gg[u] = g;
+                if (k < p.ne) {
+                  const long long er = p.perm ? (long long)__ldg(p.perm + e) : e;
+                  bp[u] = p.ea + k; off[u] = er * p.ld_ea;
+                  if (p.ea_add) ai[u] = __ldg(p.ea_add_idx + e);
+                } else if (k < p.ne + p.ns) {
+                  bp[u] = p.node + (k - p.ne); off[u] = (long long)__ldg(p.tgt + e) * p.ld_node;
+                } else {
+                  bp[u] = p.node + (k - p.ne - p.ns); off[u] = (long long)__ldg(p.src + e) * p.ld_node;
+                }
+              } else { rr[u] = r; gg[u] = g; }     // rows past the end: zeros
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < PER; ++u) {
+            f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bp[u]) {
+              const float4* s4 = reinterpret_cast<const float4*>(bp[u] + off[u]);
+              f[u][0] = __ldg(s4);
+              f[u][1] = __ldg(s4 + 1);
             }
           }
 #pragma unroll
           for (int u = 0; u < PER; ++u) {
             if (rr[u] >= 0) {
+              if (ai[u] >= 0) {
+                const float4* a4 = reinterpret_cast<const float4*>(p.ea_add + (long long)ai[u] * p.ne + (gg[u] << 3));
+                const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1);
+                f[u][0].x += a0.x; f[u][0].y += a0.y; f[u][0].z += a0.z; f[u][0].w += a0.w;
+                f[u][1].x += a1.x; f[u][1].y += a1.y; f[u][1].z += a1.z; f[u][1].w += a1.w;
+              }
               uint4 hi, lo;
               split8(reinterpret_cast<const float*>(&f[u][0]), hi, lo);
               put_a8(sA, rr[u], gg[u] << 3, hi);
-              put_a8(sA, rr[u], Kin + (gg[u] << 3), hi);
-              put_a8(sA, rr[u], 2 * Kin + (gg[u] << 3), lo);
+              put_a8(sA, rr[u], Kp + (gg[u] << 3), lo);
             }
           }
         }
-      } else
-      for (int idx = tid; idx < BM * Kin; idx += THREADS) {
-        const int r = idx / Kin, k = idx - r * Kin;
-        const long long e = e0 + r;
-        float v = 0.f;
-        if (e < p.n_edges) {
-          if (k < p.ne) v = __ldg(p.ea + e * p.ld_ea + k);
-          else if (k < p.ne + p.ns) v = __ldg(p.node + (long long)__ldg(p.tgt + e) * p.ld_node + (k - p.ne));
-          else v = __ldg(p.node + (long long)__ldg(p.src + e) * p.ld_node + (k - p.ne - p.ns));
+      } else {
+        for (int idx = tid; idx < BM * Kin; idx += THREADS) {
+          const int r = idx / Kin, k = idx - r * Kin;
+          const long long e = e0 + r;
+          float v = 0.f;
+          if (e < n_edges) {
+            if (k < p.ne) {
+              const long long er = p.perm ? (long long)__ldg(p.perm + e) : e;
+              v = __ldg(p.ea + er * p.ld_ea + k);
+              if (p.ea_add) v += __ldg(p.ea_add + (long long)__ldg(p.ea_add_idx + e) * p.ne + k);
+            } else if (k < p.ne + p.ns) v = __ldg(p.node + (long long)__ldg(p.tgt + e) * p.ld_node + (k - p.ne));
+            else v = __ldg(p.node + (long long)__ldg(p.src + e) * p.ld_node + (k - p.ne - p.ns));
+          }
+          const __nv_bfloat16 hi = __float2bfloat16(v);
+          const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+          put_a(sA, r, k, hi);
+          put_a(sA, r, Kp + k, lo);
         }
-        const __nv_bfloat16 hi = __float2bfloat16(v);
-        const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-        put_a(sA, r, k, hi);
-        put_a(sA, r, Kin + k, hi);
-        put_a(sA, r, 2 * Kin + k, lo);
       }
       if constexpr (CG == 2) asm volatile("fence.proxy.async;" ::: "memory");
       else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -442,6 +516,29 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
           }
         }
       }
+    } else if (warp == 2) {
+      // ===== L2 prefetch of the next unit's streamed inputs (edge attributes, index and vector rows) ===================
+      // The operand build of the next unit is a serial phase in which the tensor pipe idles; its loads then hit L2
+      // instead of HBM.
+      const long long nu = unit + gridDim.x / CG;
+      if (nu < n_units) {
+        const long long e0n = (nu * CG + rank) * BM;
+        for (int r = lane; r < BM; r += 32) {
+          const long long e = e0n + r;
+          if (e < n_edges) {
+            const long long er = p.perm ? (long long)__ldg(p.perm + e) : e;
+            const char* row = reinterpret_cast<const char*>(p.ea + er * p.ld_ea);
+            prefetch_l2(row);
+            if (p.ne * 4 > 128) prefetch_l2(row + 128);
+            prefetch_l2(row + p.ne * 4 - 4);
+            prefetch_l2(p.vec + 3 * er);
+          }
+        }
+        if (lane < 4 && e0n + lane * 32 < n_edges) {     // contiguous index streams: 128 x 4 B per CTA
+          prefetch_l2(p.tgt + e0n + lane * 32);
+          prefetch_l2(p.src + e0n + lane * 32);
+        }
+      }
     } else if (warp == 3 && CG == 2) {
       // ===== relay (peer CTA only): tell the leader's MMA thread that this CTA's half of a stage has landed ===========
       // (a plain bulk copy can only complete_tx on a barrier of the CTA it writes to - measured: signalling the leader's
@@ -468,12 +565,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         for (int t = -1; t < p.n_tiles; ++t, ++ma) {
           const uint32_t buf = ma & 1, aph = (ma >> 1) & 1;
           long long t0 = DBG_T();
-          mbar_wait_cg<CG>(&tempty[buf], aph ^ 1);
+          mbar_wait(&tempty[buf], aph ^ 1);
           w_te += DBG_T() - t0;
           tc_fence_after();
           const uint32_t d = tmem_base + buf * BN;
           const int nkb = (t < 0) ? p.n_kb1 : p.n_kb;
           const int nmma = (t < 0) ? n1 : sTiles[t * 8 + 1];
+          const uint4* ops = reinterpret_cast<const uint4*>(sOps + ((t < 0) ? 0 : MAX_KB * OPS_PER_KB));
           const uint32_t idesc = idesc0 | ((uint32_t)(nmma >> 3) << 17);
           for (int kb = 0; kb < nkb; ++kb, ++mc) {
             const uint32_t s = mc % STAGES, ph = (mc / STAGES) & 1;
@@ -483,11 +581,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
             w_full += DBG_T() - t0;
             t0 = DBG_T();
             tc_fence_after();
-            const uint32_t a_lo = a_lo0 + kb * (A_KB_BYTES >> 4), b_lo = b_lo0 + s * (B_STAGE_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + s * (B_STAGE_BYTES >> 4);
             if (elect_one()) {
+              const uint4 o0 = ops[kb * 2], o1 = ops[kb * 2 + 1];
+              const uint32_t op[OPS_PER_KB] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk)
-                umma_bf16_lo<CG>(d, a_lo + kk * 2, b_lo + kk * 2, idesc, (kb | kk) != 0);
+              for (int i = 0; i < OPS_PER_KB; ++i)
+                if (op[i] != 0xFFFFFFFFu)
+                  umma_bf16_lo<CG>(d, a_lo0 + (op[i] & 0x0FFFFFFFu), b_lo + (op[i] >> 28) * 2, idesc, (kb | i) != 0);
               umma_commit<CG>(&empty[s]);
               if (kb == nkb - 1) umma_commit<CG>(&tfull[buf]);
             }
@@ -503,30 +604,24 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
         }
         if (lane == 0) {
           DBG_ADD(0, DBG_T() - t_role); DBG_ADD(1, w_te); DBG_ADD(2, w_full); DBG_ADD(3, w_a);
-          DBG_ADD(13, b_issue); DBG_ADD(14, (long long)(p.n_kb1 + p.n_tiles * p.n_kb) * 4);
+          DBG_ADD(13, b_issue); DBG_ADD(14, (long long)(3 * S1 + 1) + (long long)p.n_tiles * (3 * S2 + 1));
         }
       }
     } else if (warp >= 4) {
       // ===== consumers: thread <-> edge <-> TMEM lane ===========================================================
       const int q = warp & 3, ct = q * 32 + lane;          // row of the edge tile
       const long long e = mt * BM + ct;
-      const bool valid = e < p.n_edges;
+      const bool valid = e < n_edges;
       const int src_e = valid ? __ldg(p.src + e) : 0, dst_e = valid ? __ldg(p.tgt + e) : -1;
-      const float ew_e = (valid && p.ew) ? __ldg(p.ew + e) : 1.f;
-      // runs of equal scatter targets inside the warp (rows past the end sort last)
-      const int seg_key = valid ? dst_e : 0x7fffffff;
-      const int key_dn = __shfl_down_sync(0xffffffffu, seg_key, 1), key_up = __shfl_up_sync(0xffffffffu, seg_key, 1);
-      const bool seg_sorted = p.seg_flush && __all_sync(0xffffffffu, lane == 31 || key_dn >= seg_key);
-      const bool seg_head = lane == 0 || key_up != seg_key;
-      uint32_t seg_same = 0;      // bit o: lane + 2^o belongs to the same run
-#pragma unroll
-      for (int o = 0; o < 5; ++o) {
-        const int ko = __shfl_down_sync(0xffffffffu, seg_key, 1u << o);
-        if (lane + (1 << o) < 32 && ko == seg_key) seg_same |= 1u << o;
-      }
+      const long long er = (valid && p.perm) ? (long long)__ldg(p.perm + e) : e;
+      const float ew_e = (valid && p.ew) ? __ldg(p.ew + er) : 1.f;
+      // runs of equal scatter targets inside the warp (rows past the end form their own, never flushed, runs)
+      const int key_up = __shfl_up_sync(0xffffffffu, dst_e, 1);
+      const uint32_t head_mask = __ballot_sync(0xffffffffu, lane == 0 || key_up != dst_e || !valid);
+      float* sF = sFlush + q * 48 * FLUSH_LD;
       {   // real spherical harmonics of the edge vector, component normalisation (e3nn polynomials)
-        float vx = valid ? __ldg(p.vec + 3 * e) : 1.f, vy = valid ? __ldg(p.vec + 3 * e + 1) : 0.f,
-              vz = valid ? __ldg(p.vec + 3 * e + 2) : 0.f;
+        float vx = valid ? p.vec_sign * __ldg(p.vec + 3 * er) : 1.f, vy = valid ? p.vec_sign * __ldg(p.vec + 3 * er + 1) : 0.f,
+              vz = valid ? p.vec_sign * __ldg(p.vec + 3 * er + 2) : 0.f;
         const float nrm = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
         vx /= nrm; vy /= nrm; vz /= nrm;
         const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f, s15 = 3.872983346207417f;
@@ -542,10 +637,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
       {   // hidden activations: ReLU (bias already folded), bf16 split, written back over the operand image as A'
         const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
         const long long t0 = DBG_T();
-        mbar_wait_cg<CG>(&tfull[buf], aph);
+        mbar_wait(&tfull[buf], aph);
         if (tid == 128) DBG_ADD(9, DBG_T() - t0);
         tc_fence_after();
-        const int K = p.H, kpad = p.n_kb * BK;
+        const int K = p.H, Kp = p.Hp;
         for (int c0 = 0; c0 < K; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
@@ -560,8 +655,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
                 uint4 hi, lo;
                 split8(f, hi, lo);
                 put_a8(sA, ct, k, hi);
-                put_a8(sA, ct, K + k, hi);
-                put_a8(sA, ct, 2 * K + k, lo);
+                put_a8(sA, ct, Kp + k, lo);
               }
             }
           } else {
@@ -573,13 +667,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
                 const __nv_bfloat16 hi = __float2bfloat16(hval);
                 const __nv_bfloat16 lo = __float2bfloat16(hval - __bfloat162float(hi));
                 put_a(sA, ct, k, hi);
-                put_a(sA, ct, K + k, hi);
-                put_a(sA, ct, 2 * K + k, lo);
+                put_a(sA, ct, Kp + k, lo);
               }
             }
           }
         }
-        for (int col = 3 * K; col < kpad; ++col) put_a(sA, ct, col, col < 3 * K + 2 ? one : zero);
+        put_a_tail(sA, ct, K, Kp);
         if constexpr (CG == 2) asm volatile("fence.proxy.async;" ::: "memory");
         else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
@@ -592,43 +685,44 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
       }
       float acc[48], xn[XN], M[9];
       const long long t_loop = DBG_T();
-      prefetch_x(xrow + sTiles[2], sTiles[3] * sTiles[4], xn);
+      prefetch_x(xrow + sTiles[2], sTiles[3] * sTiles[4], p.x_vec2, xn);
       for (int t = 0; t < p.n_tiles; ++t, ++ea) {
         const int* ti = sTiles + t * 8;
         const int kind = ti[0], d_in = ti[4], out_off = ti[5], flags = ti[6];
-        const int tn = (t + 1 < p.n_tiles) ? t + 1 : t;          // next tile (the last one re-requests its own rows)
+        const int tn = (t + 1 < p.n_tiles) ? t + 1 : t;          // next tile (the last one requests nothing)
         const float* xnext = xrow + sTiles[tn * 8 + 2];
         const int cnt_next = (t + 1 < p.n_tiles) ? sTiles[tn * 8 + 3] * sTiles[tn * 8 + 4] : 0;
         if (flags & 1) {
 #pragma unroll
           for (int i = 0; i < 48; ++i) acc[i] = 0.f;
         }
-        // M[i,k] = edge_weight * sum_j coef*C[i,j,k] * Y[j]  (at most 3x3 for the supported paths; row-major, stride 3),
-        // rebuilt only when the tile belongs to another path than its predecessor
+        // M[i,k] = edge_weight * sum_j coef*C[i,j,k] * Y[sh_off + j]  (at most 3x3 for the supported paths; row-major,
+        // stride 3), rebuilt only when the tile belongs to another path than its predecessor: dense table, fully unrolled
         const long long tm0 = DBG_T();
         if (flags & 4) {
-          const int dout = (kind == 0 || kind == 2) ? 1 : 3;
-          const int* me = sMent + ti[7] * 2;
+          const float* T = sMtab + ti[7] * MTAB;
+          const int sh_off = (flags >> 8) & 0xff;
+          float yb[5];
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 5; ++j) yb[j] = sY[min(sh_off + j, 8) * 128 + ct];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              float a = 0.f;
-              if (i < d_in && k < dout) {
-                const int b = me[(i * dout + k) * 2], n = me[(i * dout + k) * 2 + 1];
-                for (int tq = b; tq < b + n; ++tq) a = fmaf(sTermV[tq], sY[sTermY[tq] * 128 + ct], a);
-              }
-              M[i * 3 + k] = a * ew_e;
-            }
+          for (int ik = 0; ik < 9; ++ik) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) a = fmaf(T[ik * 5 + j], yb[j], a);
+            M[ik] = a * ew_e;
+          }
         }
         const uint32_t buf = ea & 1, aph = (ea >> 1) & 1;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+        const int nch = ti[1] >> 5;
         const long long tm1 = DBG_T();
+        unsigned long long* dbgp = (DBG && tid == 128) ? p.dbg : nullptr;
         switch (kind) {
-          case 0: tile_body<CG, 48, 1, 4>(taddr, xn, d_in, M, acc, xnext, cnt_next, &tfull[buf], aph, (DBG && tid == 128) ? p.dbg : nullptr); break;
-          case 1: tile_body<CG, 10, 3, 16>(taddr, xn, d_in, M, acc, xnext, cnt_next, &tfull[buf], aph, (DBG && tid == 128) ? p.dbg : nullptr); break;
-          case 2: tile_body<CG, 16, 1, 8>(taddr, xn, d_in, M, acc, xnext, cnt_next, &tfull[buf], aph, (DBG && tid == 128) ? p.dbg : nullptr); break;
-          default: tile_body<CG, 4, 3, 16>(taddr, xn, d_in, M, acc, xnext, cnt_next, &tfull[buf], aph, (DBG && tid == 128) ? p.dbg : nullptr); break;
+          case 0: tile_body<48, 1, 4>(taddr, nch, xn, d_in, M, acc, xnext, cnt_next, p.x_vec2, &tfull[buf], aph, dbgp); break;
+          case 1: tile_body<10, 3, 16>(taddr, nch, xn, d_in, M, acc, xnext, cnt_next, p.x_vec2, &tfull[buf], aph, dbgp); break;
+          case 2: tile_body<16, 1, 8>(taddr, nch, xn, d_in, M, acc, xnext, cnt_next, p.x_vec2, &tfull[buf], aph, dbgp); break;
+          default: tile_body<4, 3, 16>(taddr, nch, xn, d_in, M, acc, xnext, cnt_next, p.x_vec2, &tfull[buf], aph, dbgp); break;
         }
         tc_fence_before();
         __syncwarp();
@@ -641,43 +735,41 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
           if (kind == 0) DBG_ADD(17, tm2 - tm1); else DBG_ADD(18, tm2 - tm1);
           if (kind == 0) DBG_ADD(19, 1); else DBG_ADD(20, 1);
         }
-        if (flags & 2) {   // end of an output irrep: scatter-add, pre-reduced over runs of equal targets within the warp
+        if (flags & 2) {
+          // end of an output irrep: scatter-add.  The warp's 32 x nacc partial results are transposed through shared memory
+          // (padded rows: conflict-free both ways); lane i then walks the 32 edges, summing runs of equal targets (CSR order
+          // makes them contiguous; unsorted input just yields runs of length one) and issues ONE fully coalesced RED.ADD per
+          // run for output values i = 0..31 (a second pass covers values 32..47).
           const int nacc = (kind == 0) ? 48 : (kind == 1 ? 30 : (kind == 2 ? 16 : 12));
-          if (seg_sorted) {
-            // CSR order: equal targets are contiguous lanes -> segmented shuffle reduction, one atomic per run and value
-            // (the edges of a 24-neighbour receptor node span at most two warps: ~2-3 atomics instead of 32)
 #pragma unroll
-            for (int i = 0; i < 48; ++i) {
-              if (i < nacc) {
-                float v = acc[i];
+          for (int i = 0; i < 48; ++i)
+            if (i < nacc) sF[i * FLUSH_LD + lane] = acc[i];
+          __syncwarp();
+          for (int i0 = 0; i0 < nacc; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < nacc;
+            const float* col = sF + (act ? i : 0) * FLUSH_LD;
+            float s = 0.f;
 #pragma unroll
-                for (int o = 0; o < 5; ++o) {
-                  const float tv = __shfl_down_sync(0xffffffffu, v, 1u << o);
-                  if ((seg_same >> o) & 1) v += tv;
-                }
-                if (seg_head && valid) atomicAdd(p.sum + (long long)dst_e * p.d_out + out_off + i, v);
+            for (int le = 0; le < 32; ++le) {
+              s += col[le];
+              if (le == 31 || ((head_mask >> (le + 1)) & 1)) {          // warp-uniform: last edge of a run
+                const int d = __shfl_sync(0xffffffffu, dst_e, le);
+                if (d >= 0 && act) atomicAdd(p.sum + (long long)d * p.d_out + out_off + i, s);
+                s = 0.f;
               }
             }
-          } else if (valid) {
-            float* srow = p.sum + (long long)dst_e * p.d_out + out_off;
-#pragma unroll
-            for (int i = 0; i < 48; ++i)
-              if (i < nacc) atomicAdd(srow + i, acc[i]);
           }
+          __syncwarp();
           if (DBG && tid == 128) DBG_ADD(21, DBG_T() - tm2);
         }
       }
       if (tid == 128) DBG_ADD(8, DBG_T() - t_loop);
-      if (p.cnt) {
-        if (seg_sorted) {
-          float v = 1.f;
-#pragma unroll
-          for (int o = 0; o < 5; ++o) {
-            const float tv = __shfl_down_sync(0xffffffffu, v, 1u << o);
-            if ((seg_same >> o) & 1) v += tv;
-          }
-          if (seg_head && valid) atomicAdd(p.cnt + dst_e, v);
-        } else if (valid) atomicAdd(p.cnt + dst_e, 1.f);
+      if (p.cnt) {       // edge counts per target: one atomic per run, issued by the run's first lane
+        const bool head = (head_mask >> lane) & 1;
+        const uint32_t above = (lane == 31) ? 0u : (head_mask >> (lane + 1));
+        const int run_len = above ? __ffs(above) : 32 - lane;
+        if (head && valid) atomicAdd(p.cnt + dst_e, (float)run_len);
       }
     }
     if (tid == 0) { DBG_ADD(11, DBG_T() - t_unit); DBG_ADD(12, 1); }
@@ -693,24 +785,37 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
   }
 }
 
-}  // namespace
+// per-device state: debug counters and the one-time opt-in to > 48 KB of dynamic shared memory
+constexpr int MAX_DEVICES = 64;
+struct DeviceState {
+  bool attr_done = false;
+  bool dbg_init = false;
+  unsigned long long* dbg = nullptr;
+};
+DeviceState g_dev[MAX_DEVICES];
 
-static unsigned long long* fused_debug_buffer() {
-  static unsigned long long* buf = [] {
+unsigned long long* fused_debug_buffer(int dev) {
+  if (dev < 0 || dev >= MAX_DEVICES) return nullptr;
+  DeviceState& st = g_dev[dev];
+  if (!st.dbg_init) {
+    st.dbg_init = true;
     const char* e = getenv("DDB200_FUSED_DEBUG");
-    unsigned long long* b = nullptr;
-    if (e && atoi(e) != 0 && cudaMalloc(&b, 32 * sizeof(unsigned long long)) == cudaSuccess)
-      cudaMemset(b, 0, 32 * sizeof(unsigned long long));
-    return b;
-  }();
-  return buf;
+    if (e && atoi(e) != 0 && cudaMalloc(&st.dbg, 32 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(st.dbg, 0, 32 * sizeof(unsigned long long));
+  }
+  return st.dbg;
 }
 
-// Diagnostics (DDB200_FUSED_DEBUG=1 only): copies the 32 clock counters of the fused kernel's warp roles to `out` and
-// clears them.  [0] MMA role total, [1] wait accumulator-free, [2] wait B stage, [3] wait A', [5] producer wait stage-free,
-// [8] consumer tile loop, [9] consumer wait hidden, [10] A0 build, [11] unit total, [12] units.  Synchronises the device.
+}  // namespace
+
+// Diagnostics (DDB200_FUSED_DEBUG=1 only): copies the 32 clock counters of the fused kernel's warp roles (current device) to
+// `out` and clears them.  [0] MMA role total, [1] wait accumulator-free, [2] wait B stage, [3] wait A', [5] producer wait
+// stage-free, [8] consumer tile loop, [9] consumer wait hidden, [10] A0 build, [11] unit total, [12] units (counted per CTA).
+// Synchronises the device.
 extern "C" int ddb200_fused_debug_read(uint64_t* out) {
-  unsigned long long* b = fused_debug_buffer();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  unsigned long long* b = fused_debug_buffer(dev);
   if (!b || !out) return DDB200_EINVAL;
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(out, b, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -718,56 +823,56 @@ extern "C" int ddb200_fused_debug_read(uint64_t* out) {
   return (int)e;
 }
 
-extern "C" int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, const float* node, int64_t ld_node, int ns,
-                                 const int32_t* tgt, const int32_t* src, const void* w1_images, int hidden,
-                                 const void* w2_images, const int32_t* tiles, int n_tiles, const int32_t* ment, int n_ment,
-                                 const int32_t* term_y, const float* term_v, int n_terms, const float* x, int64_t ld_x,
-                                 const float* edge_vec, const float* edge_weight, int sh_lmax, int64_t n_edges,
-                                 float* sum, int d_out, float* cnt, void* stream) {
-  if (!edge_attr || !w1_images || !w2_images || !tiles || !ment || !term_y || !term_v || !x || !edge_vec || !sum ||
-      !tgt || !src || n_edges < 0 || ne <= 0 || ns < 0 || hidden <= 0 || n_tiles <= 0 || d_out <= 0)
+extern "C" int ddb200_fused_conv(const ddb200_fused_args* a, void* stream) {
+  if (!a || !a->edge_attr || !a->w1_images || !a->w2_images || !a->tiles || !a->mtab || !a->x || !a->edge_vec || !a->sum ||
+      !a->tgt || !a->src || a->n_edges < 0 || a->ne <= 0 || a->ns < 0 || a->hidden <= 0 || a->n_tiles <= 0 || a->d_out <= 0)
     return DDB200_EINVAL;
-  if (ns > 0 && (!node || ld_node < ns)) return DDB200_EINVAL;
-  if (n_tiles > MAX_TILES || n_ment > MAX_MENT || n_terms > MAX_TERMS || sh_lmax < 0 || sh_lmax > 2) return DDB200_EINVAL;
-  const int K1 = ne + 2 * ns;
-  const int n_kb = (3 * hidden + 2 + BK - 1) / BK, n_kb1 = (3 * K1 + 2 + BK - 1) / BK;
-  if (n_kb > MAX_KB || n_kb1 > MAX_KB || hidden > MAX_N) return DDB200_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(w1_images) & 127) || (reinterpret_cast<uintptr_t>(w2_images) & 127)) return DDB200_EINVAL;
-  if (n_edges == 0) return 0;
+  if (a->ns > 0 && (!a->node || a->ld_node < a->ns)) return DDB200_EINVAL;
+  if (a->n_tiles > MAX_TILES || a->n_paths <= 0 || a->n_paths > MAX_PATHS || a->sh_lmax < 0 || a->sh_lmax > 2)
+    return DDB200_EINVAL;
+  if ((a->ea_add == nullptr) != (a->ea_add_idx == nullptr)) return DDB200_EINVAL;
+  const int K1 = a->ne + 2 * a->ns, H = a->hidden;
+  const int K1p = (K1 + 15) / 16 * 16, Hp = (H + 15) / 16 * 16;
+  const int n_kb = (2 * Hp + 16 + BK - 1) / BK, n_kb1 = (2 * K1p + 16 + BK - 1) / BK;
+  if (n_kb > MAX_KB || n_kb1 > MAX_KB || H > MAX_N) return DDB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(a->w1_images) & 127) || (reinterpret_cast<uintptr_t>(a->w2_images) & 127)) return DDB200_EINVAL;
+  if (a->n_edges == 0) return 0;
   FusedParams p = {};
-  p.ea = edge_attr; p.ld_ea = ld_ea; p.ne = ne; p.node = node; p.ld_node = ld_node; p.ns = ns; p.tgt = tgt; p.src = src;
-  p.w1img = reinterpret_cast<const __nv_bfloat16*>(w1_images); p.K1 = K1; p.n_kb1 = n_kb1; p.H = hidden; p.n_kb = n_kb;
-  p.w2img = reinterpret_cast<const __nv_bfloat16*>(w2_images); p.tiles = tiles; p.n_tiles = n_tiles;
-  p.ment = ment; p.term_y = term_y; p.term_v = term_v; p.n_ment = n_ment; p.n_terms = n_terms;
-  p.x = x; p.ld_x = ld_x; p.vec = edge_vec; p.ew = edge_weight; p.lmax = sh_lmax; p.sum = sum; p.d_out = d_out; p.cnt = cnt;
-  p.n_edges = n_edges;
-  p.dbg = fused_debug_buffer();
-  static const int seg_env = [] { const char* e = getenv("DDB200_FUSED_SEGFLUSH"); return e ? atoi(e) : 1; }();
-  p.seg_flush = seg_env;
-  static const int noload = [] { const char* e = getenv("DDB200_FUSED_NOLOAD"); return e ? atoi(e) : 0; }();
-  p.dbg_noload = p.dbg ? noload : 0;
-  const int n_kb_max = n_kb > n_kb1 ? n_kb : n_kb1;
+  p.ea = a->edge_attr; p.ld_ea = a->ld_ea; p.ne = a->ne; p.node = a->node; p.ld_node = a->ld_node; p.ns = a->ns;
+  p.tgt = a->tgt; p.src = a->src; p.perm = a->edge_perm; p.ea_add = a->ea_add; p.ea_add_idx = a->ea_add_idx;
+  p.vec_sign = a->vec_sign == 0.f ? 1.f : a->vec_sign;
+  p.w1img = reinterpret_cast<const __nv_bfloat16*>(a->w1_images); p.K1 = K1; p.K1p = K1p; p.n_kb1 = n_kb1;
+  p.H = H; p.Hp = Hp; p.n_kb = n_kb;
+  p.w2img = reinterpret_cast<const __nv_bfloat16*>(a->w2_images); p.tiles = a->tiles; p.n_tiles = a->n_tiles;
+  p.mtab = a->mtab; p.n_paths = a->n_paths;
+  p.x = a->x; p.ld_x = a->ld_x; p.x_vec2 = (a->x_pairs_ok && (a->ld_x & 1) == 0 && (reinterpret_cast<uintptr_t>(a->x) & 7) == 0) ? 1 : 0;
+  p.vec = a->edge_vec; p.ew = a->edge_weight; p.lmax = a->sh_lmax; p.sum = a->sum; p.d_out = a->d_out; p.cnt = a->cnt;
+  p.n_edges = a->n_edges; p.n_edges_dev = a->n_edges_dev;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
+  if (dev < 0 || dev >= MAX_DEVICES) return DDB200_EINVAL;
+  p.dbg = fused_debug_buffer(dev);
+  static const int noload = [] { const char* e = getenv("DDB200_FUSED_NOLOAD"); return e ? atoi(e) : 0; }();
+  p.dbg_noload = p.dbg ? noload : 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long n_mtiles = (n_edges + BM - 1) / BM;
-  // CTA pairs (tcgen05 cta_group::2) unless disabled; every tile width of the plan (192/160/256/64, hidden rounded to 16)
+  const long long n_mtiles = (a->n_edges + BM - 1) / BM;
+  // CTA pairs (tcgen05 cta_group::2) unless disabled; every tile width of the plan (multiples of 32, hidden rounded to 16)
   // splits into two halves of whole 8-row swizzle atoms
   static const int pair_env = [] { const char* e = getenv("DDB200_FUSED_CTA_PAIR"); return e ? atoi(e) : 1; }();
   const bool pair = pair_env != 0 && n_mtiles >= 2;
-  const size_t fixed = 9 * 128 * 4 + MAX_TILES * 8 * 4 + MAX_MENT * 2 * 4 + MAX_TERMS * 8 + 32 * sizeof(uint64_t) + 1024;
-  const size_t smem = (size_t)n_kb_max * A_KB_BYTES + fixed +
+  const size_t fixed = (9 * 128 + 4 * 48 * FLUSH_LD + MAX_PATHS * MTAB) * 4 + MAX_TILES * 8 * 4 +
+                       2 * MAX_KB * OPS_PER_KB * 4 + 36 * sizeof(uint64_t) + 1024;
+  const size_t smem = (size_t)MAX_KA * A_KB_BYTES + fixed +
                       (pair ? Ring<2>::STAGES * Ring<2>::STAGE_BYTES : Ring<1>::STAGES * Ring<1>::STAGE_BYTES);
   if (smem > 227 * 1024) return DDB200_ESMEM;
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!g_dev[dev].attr_done) {      // the opt-in is a per-device attribute
     cudaError_t e = cudaSuccess;
     const void* fns[4] = {(const void*)fused_conv_kernel<1, false>, (const void*)fused_conv_kernel<2, false>,
                           (const void*)fused_conv_kernel<1, true>, (const void*)fused_conv_kernel<2, true>};
     for (int i = 0; i < 4 && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    g_dev[dev].attr_done = true;
   }
   if (!pair) {
     const unsigned grid = (unsigned)(n_mtiles < sms ? n_mtiles : sms);

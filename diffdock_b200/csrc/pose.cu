@@ -82,14 +82,55 @@ __device__ void jacobi3(double A[3][3], double V[3][3], double w[3]) {
   for (int i = 0; i < 3; ++i) w[i] = A[i][i];
 }
 
-__global__ void pose_update_kernel(const float* __restrict__ pos, int n_atoms, int n_bonds,
+// ---- counter-based noise (Philox4x32-10, Salmon et al. 2011): one stream per pose, keyed by (seed, complex id, pose id) and
+// indexed by (step, degree of freedom), so a sampling run draws the same noise whatever the batch split or GPU count
+// (SURVEY.md section 8(e)).  The reference draws torch.normal blocks per batch (utils/sampling.py:140-145).
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// four standard normals from one Philox block (Box-Muller on two pairs of 24-bit uniforms in (0, 1))
+__device__ __forceinline__ void philox_normal4(uint64_t seed, long long pose_key, uint32_t step, uint32_t block, float z[4]) {
+  uint32_t c[4] = {(uint32_t)pose_key, (uint32_t)((unsigned long long)pose_key >> 32), step, block};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = (float)(c[2 * h] >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;      // (k + 0.5) / 2^24
+    const float u2 = (float)(c[2 * h + 1] >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
+  }
+}
+
+struct PoseNoise {
+  const float* coef_dev;        // optional device table [*, 6]; row *step_dev (or 0)
+  const int* step_dev;          // optional device scalar
+  unsigned long long seed;      // Philox key
+  const long long* pose_key;    // optional [n_poses]: (complex id << 32) | pose id  -> in-kernel noise
+  int philox;
+};
+
+__global__ void pose_update_kernel(const float* pos, int n_atoms, int n_bonds,
                                    const int* __restrict__ bond_u, const int* __restrict__ bond_v,
                                    const unsigned char* __restrict__ mask, const float* __restrict__ tr_score,
                                    const float* __restrict__ rot_score, const float* __restrict__ tor_score,
                                    const float* __restrict__ tr_z, const float* __restrict__ rot_z,
                                    const float* __restrict__ tor_z, float a_tr, float c_tr, float a_rot, float c_rot,
-                                   float a_tor, float c_tor, int use_torsion, float* __restrict__ out) {
+                                   float a_tor, float c_tor, int use_torsion, const PoseNoise nz, float* out) {
   extern __shared__ float sm[];
+  const int step = nz.step_dev ? *nz.step_dev : 0;
+  if (nz.coef_dev) {         // SDE coefficients of this step from a device table: the host never touches the step loop
+    const float* cf = nz.coef_dev + 6 * (long long)step;
+    a_tr = cf[0]; c_tr = cf[1]; a_rot = cf[2]; c_rot = cf[3]; a_tor = cf[4]; c_tor = cf[5];
+  }
   float* rig = sm;                         // [n_atoms*3]
   float* flex = rig + 3 * n_atoms;         // [n_atoms*3]
   float* mat = flex + 3 * n_atoms;         // [16]
@@ -105,10 +146,17 @@ __global__ void pose_update_kernel(const float* __restrict__ pos, int n_atoms, i
   const float cx = (float)(part[0] / n_atoms), cy = (float)(part[1] / n_atoms), cz = (float)(part[2] / n_atoms);
 
   if (tid == 0) {
-    const float zx = rot_z ? rot_z[3 * b] : 0.f, zy = rot_z ? rot_z[3 * b + 1] : 0.f, zz = rot_z ? rot_z[3 * b + 2] : 0.f;
-    axis_angle_to_matrix(a_rot * rot_score[3 * b] + c_rot * zx, a_rot * rot_score[3 * b + 1] + c_rot * zy,
-                         a_rot * rot_score[3 * b + 2] + c_rot * zz, mat);
-    for (int d = 0; d < 3; ++d) mat[9 + d] = a_tr * tr_score[3 * b + d] + c_tr * (tr_z ? tr_z[3 * b + d] : 0.f);
+    float zr[4] = {0.f, 0.f, 0.f, 0.f}, zt[4] = {0.f, 0.f, 0.f, 0.f};
+    if (nz.philox) {
+      philox_normal4(nz.seed, nz.pose_key[b], (uint32_t)step, 0u, zt);
+      philox_normal4(nz.seed, nz.pose_key[b], (uint32_t)step, 1u, zr);
+    } else {
+      if (rot_z) { zr[0] = rot_z[3 * b]; zr[1] = rot_z[3 * b + 1]; zr[2] = rot_z[3 * b + 2]; }
+      if (tr_z) { zt[0] = tr_z[3 * b]; zt[1] = tr_z[3 * b + 1]; zt[2] = tr_z[3 * b + 2]; }
+    }
+    axis_angle_to_matrix(a_rot * rot_score[3 * b] + c_rot * zr[0], a_rot * rot_score[3 * b + 1] + c_rot * zr[1],
+                         a_rot * rot_score[3 * b + 2] + c_rot * zr[2], mat);
+    for (int d = 0; d < 3; ++d) mat[9 + d] = a_tr * tr_score[3 * b + d] + c_tr * zt[d];
   }
   __syncthreads();
   for (int i = tid; i < n_atoms; i += nt) {
@@ -133,7 +181,13 @@ __global__ void pose_update_kernel(const float* __restrict__ pos, int n_atoms, i
     if (tid == 0) {
       float ax = flex[3 * u] - pvx, ay = flex[3 * u + 1] - pvy, az = flex[3 * u + 2] - pvz;
       const float nrm = sqrtf(ax * ax + ay * ay + az * az);
-      const float ang = a_tor * tor_score[(size_t)b * n_bonds + r] + c_tor * (tor_z ? tor_z[(size_t)b * n_bonds + r] : 0.f);
+      float zq = tor_z ? tor_z[(size_t)b * n_bonds + r] : 0.f;
+      if (nz.philox) {
+        float z4[4];
+        philox_normal4(nz.seed, nz.pose_key[b], (uint32_t)step, 2u + (uint32_t)(r >> 2), z4);
+        zq = z4[r & 3];
+      }
+      const float ang = a_tor * tor_score[(size_t)b * n_bonds + r] + c_tor * zq;
       ax = ax / nrm * ang; ay = ay / nrm * ang; az = az / nrm * ang;
       axis_angle_to_matrix(ax, ay, az, mat);
     }
@@ -229,6 +283,61 @@ extern "C" int ddb200_pose_update(const float* pos, int64_t n_poses, int n_atoms
   }
   pose_update_kernel<<<(unsigned)n_poses, 128, smem, (cudaStream_t)stream>>>(
       pos, n_atoms, n_bonds, bond_u, bond_v, mask_rotate, tr_score, rot_score, tor_score, tr_z, rot_z, tor_z, coef6[0],
-      coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], use_torsion, out_pos);
+      coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], use_torsion, PoseNoise{}, out_pos);
+  return (int)cudaGetLastError();
+}
+
+// Same update with the step's SDE coefficients read from DEVICE memory (row *step_dev of coef_table [n_steps, 6]; step_dev
+// NULL = row 0) and, if pose_key != NULL, the noise drawn in-kernel from Philox4x32-10 keyed by (seed, pose_key[b]) at
+// counter (step, dof) - no host value enters the launch, so the whole reverse-diffusion step can sit in a CUDA graph, and a
+// pose's noise does not depend on how poses are batched or sharded.  out_pos may alias pos (each pose is read completely
+// before it is written).
+extern "C" int ddb200_pose_update_dev(const float* pos, int64_t n_poses, int n_atoms, int n_bonds, const int32_t* bond_u,
+                                      const int32_t* bond_v, const uint8_t* mask_rotate, const float* tr_score,
+                                      const float* rot_score, const float* tor_score, const float* tr_z,
+                                      const float* rot_z, const float* tor_z, const float* coef_table,
+                                      const int32_t* step_dev, uint64_t seed, const int64_t* pose_key, int use_torsion,
+                                      float* out_pos, void* stream) {
+  if (!pos || !out_pos || !tr_score || !rot_score || !coef_table || n_poses < 0 || n_atoms <= 0 || n_bonds < 0)
+    return DDB200_EINVAL;
+  if (use_torsion && n_bonds > 0 && (!bond_u || !bond_v || !mask_rotate || !tor_score)) return DDB200_EINVAL;
+  if (n_poses == 0) return 0;
+  const size_t smem = sizeof(float) * (6 * (size_t)n_atoms + 16) + sizeof(double) * (32 * 9 + 16) + 16;
+  if (smem > 200 * 1024) return DDB200_ESMEM;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(pose_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  PoseNoise nz;
+  nz.coef_dev = coef_table; nz.step_dev = step_dev; nz.seed = seed;
+  nz.pose_key = reinterpret_cast<const long long*>(pose_key); nz.philox = pose_key != nullptr;
+  pose_update_kernel<<<(unsigned)n_poses, 128, smem, (cudaStream_t)stream>>>(
+      pos, n_atoms, n_bonds, bond_u, bond_v, mask_rotate, tr_score, rot_score, tor_score, tr_z, rot_z, tor_z, 0.f, 0.f, 0.f,
+      0.f, 0.f, 0.f, use_torsion, nz, out_pos);
+  return (int)cudaGetLastError();
+}
+
+// Diagnostics / tests: out[4 * i .. 4 * i + 3] = the four normals of Philox block (seed, pose_key, step, block0 + i).
+namespace {
+__global__ void philox_probe_kernel(unsigned long long seed, long long pose_key, uint32_t step, uint32_t block0, int n,
+                                    float* out, uint32_t* raw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float z[4];
+  philox_normal4(seed, pose_key, step, block0 + i, z);
+  for (int j = 0; j < 4; ++j) out[4 * i + j] = z[j];
+  if (raw) {
+    uint32_t c[4] = {(uint32_t)pose_key, (uint32_t)((unsigned long long)pose_key >> 32), step, block0 + (uint32_t)i};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int j = 0; j < 4; ++j) raw[4 * i + j] = c[j];
+  }
+}
+}  // namespace
+extern "C" int ddb200_philox_probe(uint64_t seed, int64_t pose_key, uint32_t step, uint32_t block0, int n_blocks,
+                                   float* out_normals, uint32_t* out_raw, void* stream) {
+  if (!out_normals || n_blocks < 0) return DDB200_EINVAL;
+  if (n_blocks == 0) return 0;
+  philox_probe_kernel<<<(n_blocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, pose_key, step, block0, n_blocks,
+                                                                                 out_normals, out_raw);
   return (int)cudaGetLastError();
 }

@@ -34,17 +34,26 @@ def all_gather_positions(local: torch.Tensor, n_total: int, group=None) -> torch
     return torch.cat(out, 0)
 
 
-def sample_sharded(data_list: Sequence, sampler: Callable[[List], List], group=None) -> torch.Tensor:
+def sample_sharded(data_list: Sequence, sampler: Callable[[List], List], group=None, device=None,
+                   dtype=torch.float32) -> torch.Tensor:
     """Runs ``sampler(local_block)`` (e.g. a partial of diffdock_b200.sampling.sampling) on this rank's block of poses of
-    one complex and returns the final coordinates of ALL poses, [len(data_list), n_atoms, 3], on every rank."""
+    one complex and returns the final coordinates of ALL poses, [len(data_list), n_atoms, 3], on every rank.
+    ``device`` / ``dtype`` fix where the gathered tensor lives on EVERY rank (default: the current CUDA device under NCCL,
+    the CPU otherwise): a rank whose block is empty (fewer poses than ranks) must still enter the collective with a
+    buffer on the same kind of device and of the same dtype as its peers."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if device is None:
+        nccl = dist.is_initialized() and dist.get_backend(group) == 'nccl'
+        device = torch.device('cuda', torch.cuda.current_device()) if nccl else torch.device('cpu')
     lo, hi = shard_bounds(len(data_list), rank, world)
     block = list(data_list[lo:hi])
     done = sampler(block) if block else []
     n_atoms = data_list[0]['ligand'].pos.shape[0]
-    ref = done[0]['ligand'].pos if done else data_list[0]['ligand'].pos
-    local = torch.stack([d['ligand'].pos for d in done]) if done else ref.new_zeros((0, n_atoms, 3))
+    if done:
+        local = torch.stack([d['ligand'].pos for d in done]).to(device=device, dtype=dtype)
+    else:
+        local = torch.zeros((0, n_atoms, 3), device=device, dtype=dtype)
     if world == 1:
         return local
     return all_gather_positions(local, len(data_list), group)

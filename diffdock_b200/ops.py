@@ -42,14 +42,14 @@ class _Profile:
 
     def reset(self, enabled=False):
         self.enabled, self.pairs, self.bytes, self.all_launches = enabled, [], 0, 0
-        self.fused_pairs, self.fused_bytes, self.fused_flops = [], 0, 0
+        self.fused_pairs, self.fused_bytes, self.fused_flops, self.fused_alg_flops = [], 0, 0, 0
 
     def summary(self):
         torch.cuda.synchronize()
         return {'launches': len(self.pairs), 'ms': sum(a.elapsed_time(b) for a, b in self.pairs), 'bytes': self.bytes,
                 'all_launches': self.all_launches, 'fused_launches': len(self.fused_pairs),
                 'fused_ms': sum(a.elapsed_time(b) for a, b in self.fused_pairs), 'fused_bytes': self.fused_bytes,
-                'fused_flops': self.fused_flops}
+                'fused_flops': self.fused_flops, 'fused_alg_flops': self.fused_alg_flops}
 
 
 PROFILE = _Profile()
@@ -186,5 +186,100 @@ def pose_update(pos, n_poses, bond_u, bond_v, mask_rotate_u8, tr_score, rot_scor
                                        _ptr(tr_z), _ptr(rot_z), _ptr(tor_z), C.cast(c, C.c_void_p),
                                        1 if use_torsion else 0, _ptr(out), _stream())
     _lib.check(rc, 'ddb200_pose_update')
+    PROFILE.all_launches += 1
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sync-free graph construction: upper-bound buffers + the live edge count in device memory (no .item())
+def radius_count(x, y, x_ptr, y_batch32, r=1.0, r_per_graph=None, max_num_neighbors=32, exclude_self=False):
+    """count[j] = neighbours of y_j among the x of its complex (ddb200_radius_count); int32, no host sync."""
+    _need_cuda(x, y, x_ptr, y_batch32)
+    assert x.dtype == torch.float32 and y.dtype == torch.float32 and x.is_contiguous() and y.is_contiguous()
+    assert y_batch32.dtype == torch.int32 and x_ptr.dtype == torch.int32
+    n_y = y.shape[0]
+    count = torch.empty(n_y, dtype=torch.int32, device=x.device)
+    rc = _lib.lib().ddb200_radius_count(_ptr(x), _ptr(y), _ptr(x_ptr), _ptr(y_batch32), _ptr(r_per_graph), float(r), n_y,
+                                        int(max_num_neighbors), int(exclude_self), _ptr(count), _stream())
+    _lib.check(rc, 'ddb200_radius_count')
+    PROFILE.all_launches += 1
+    return count
+
+
+def graph_fill(x, y, x_ptr, y_batch32, row_start, capacity, r=1.0, r_per_graph=None, max_num_neighbors=32,
+               exclude_self=False, pre_ptr=None, pre_col=None, want_vec=True, want_eid=False, slot_out=None, slot_in=None,
+               y_ptr=None, slot_ld=0, want_perm=False, row_offset=0, col_offset=0, fill_row=None):
+    """Fill pass into buffers of ``capacity`` edges (ddb200_graph_fill).  Returns (row, col, vec | None, eid | None,
+    perm | None); entries beyond the live count keep their initial value: ``fill_row`` for row (None = uninitialised),
+    0 for col / perm, (1, 0, 0) for vec, -1 for eid - valid operands for padded library ops."""
+    dev = x.device
+    n_y = y.shape[0]
+    cap = max(int(capacity), 1)
+    init = fill_row is not None
+    row = torch.full((cap,), int(fill_row), dtype=torch.int32, device=dev) if init else torch.empty(cap, dtype=torch.int32, device=dev)
+    col = torch.zeros(cap, dtype=torch.int32, device=dev) if init else torch.empty(cap, dtype=torch.int32, device=dev)
+    vec = eid = perm = None
+    if want_vec:
+        vec = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+        if init:
+            vec.zero_()
+            vec[:, 0] = 1.0
+    if want_eid:
+        eid = torch.full((cap,), -1, dtype=torch.int32, device=dev)
+    if want_perm:
+        perm = torch.zeros(cap, dtype=torch.int32, device=dev) if init else torch.empty(cap, dtype=torch.int32, device=dev)
+    rc = _lib.lib().ddb200_graph_fill(_ptr(x), _ptr(y), _ptr(x_ptr), _ptr(y_batch32), _ptr(r_per_graph), float(r), n_y,
+                                      int(max_num_neighbors), int(exclude_self), _ptr(row_start), _ptr(pre_ptr),
+                                      _ptr(pre_col), _ptr(row), _ptr(col), _ptr(vec), _ptr(eid), _ptr(slot_out),
+                                      _ptr(slot_in), _ptr(y_ptr), int(slot_ld), _ptr(perm), int(row_offset),
+                                      int(col_offset), _stream())
+    _lib.check(rc, 'ddb200_graph_fill')
+    PROFILE.all_launches += 1
+    return row, col, vec, eid, perm
+
+
+EDGE_EMBED_SHAPES = {(64, 48), (32, 48), (64, 32), (32, 32), (64, 24), (32, 24), (64, 16), (32, 16), (16, 16), (8, 16),
+                     (16, 24), (8, 24)}
+
+
+def edge_embed(edge_vec, edge_row, u, w1_rbf, w2, b2, rbf_offset, rbf_coeff, n_edges_dev, out=None):
+    """out[e] = W2 relu(u[edge_row[e]] + W1_rbf rbf(|edge_vec[e]|)) + b2 for e < *n_edges_dev (ddb200_edge_embed)."""
+    _need_cuda(edge_vec, edge_row, u, w1_rbf, w2, b2)
+    cap, ns, D = edge_vec.shape[0], u.shape[1], w1_rbf.shape[1]
+    assert (D, ns) in EDGE_EMBED_SHAPES
+    for t in (edge_vec, u, w1_rbf, w2, b2, rbf_offset):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert edge_row.dtype == torch.int32 and w1_rbf.shape[0] == ns and tuple(w2.shape) == (ns, ns) and rbf_offset.shape[0] == D
+    if out is None:
+        out = torch.empty((cap, ns), dtype=torch.float32, device=edge_vec.device)
+    rc = _lib.lib().ddb200_edge_embed(_ptr(edge_vec), _ptr(edge_row), _ptr(u), _ptr(w1_rbf), _ptr(w2), _ptr(b2), D, ns,
+                                      _ptr(rbf_offset), float(rbf_coeff), cap, _ptr(n_edges_dev), _ptr(out), _stream())
+    _lib.check(rc, 'ddb200_edge_embed')
+    PROFILE.all_launches += 1
+    return out
+
+
+def pose_update_dev(pos, n_poses, bond_u, bond_v, mask_rotate_u8, tr_score, rot_score, tor_score, coef_table, step_dev=None,
+                    tr_z=None, rot_z=None, tor_z=None, seed=0, pose_key=None, use_torsion=True, out=None):
+    """ddb200_pose_update_dev: SDE coefficients from a device table row, optional in-kernel Philox noise; ``out`` may be
+    ``pos`` itself (in place)."""
+    _need_cuda(pos, tr_score, rot_score, coef_table)
+    assert pos.dtype == torch.float32 and pos.is_contiguous() and coef_table.dtype == torch.float32 and coef_table.is_contiguous()
+    n_atoms = pos.shape[0] // n_poses
+    n_bonds = int(bond_u.shape[0]) if bond_u is not None else 0
+    f = lambda t: t.float().contiguous() if t is not None else None
+    tr_score, rot_score, tor_score, tr_z, rot_z, tor_z = map(f, (tr_score, rot_score, tor_score, tr_z, rot_z, tor_z))
+    if out is None:
+        out = torch.empty_like(pos)
+    if pose_key is not None:
+        assert pose_key.dtype == torch.int64 and pose_key.is_cuda and pose_key.shape[0] >= n_poses
+    if step_dev is not None:
+        assert step_dev.dtype == torch.int32 and step_dev.is_cuda
+    rc = _lib.lib().ddb200_pose_update_dev(_ptr(pos), n_poses, n_atoms, n_bonds, _ptr(bond_u), _ptr(bond_v),
+                                           _ptr(mask_rotate_u8), _ptr(tr_score), _ptr(rot_score), _ptr(tor_score),
+                                           _ptr(tr_z), _ptr(rot_z), _ptr(tor_z), _ptr(coef_table), _ptr(step_dev),
+                                           C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _ptr(pose_key),
+                                           1 if use_torsion else 0, _ptr(out), _stream())
+    _lib.check(rc, 'ddb200_pose_update_dev')
     PROFILE.all_launches += 1
     return out

@@ -17,8 +17,19 @@ from .tp_table import build_table
 
 ACTIVATIONS = {'relu': nn.ReLU, 'silu': nn.SiLU}
 
-# upper bound on the bytes of per-edge tensor-product weights materialised at once (edges are processed in blocks)
-WEIGHT_BLOCK_BYTES = 16 << 30
+# upper bound on the bytes of per-edge tensor-product weights materialised at once by the streaming path (edges are
+# processed in blocks); additionally capped by a quarter of the free device memory at call time
+WEIGHT_BLOCK_BYTES = 2 << 30
+
+
+def _weight_block_edges(weight_numel_padded, device):
+    cap = WEIGHT_BLOCK_BYTES
+    try:
+        free, _ = torch.cuda.mem_get_info(device)
+        cap = min(cap, max(free // 4, 64 << 20))
+    except Exception:
+        pass
+    return max(1024, cap // (4 * weight_numel_padded))
 
 
 def get_irrep_seq(ns, nv, use_second_order_repr, reduce_pseudoscalars):
@@ -214,7 +225,7 @@ class TensorProductConvLayer(nn.Module):
     # -- forward -------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0,
-                edge_vec=None, assume_sorted=False, gather_scalars=0):
+                edge_vec=None, assume_sorted=False, gather_scalars=0, _conv_only=False):
         """Reference signature (models/tensor_layers.py:309) plus optional extensions:
         ``edge_vec`` [E,3]: evaluate the spherical harmonics in-kernel from the edge vectors (``edge_sh`` is ignored);
         ``assume_sorted``: every edge group is already sorted by target node ``edge_index[0]``;
@@ -233,10 +244,11 @@ class TensorProductConvLayer(nn.Module):
             x = x.contiguous()
         n_out = int(out_nodes) if out_nodes else x.shape[0]
         E = edge_index.shape[1]
-        scale, shift = self.batch_norm.fold() if self.batch_norm is not None else (None, None)
+        scale, shift = self.batch_norm.fold() if (self.batch_norm is not None and not _conv_only) else (None, None)
+        residual = self.residual and not _conv_only      # _conv_only: the bare convolution (OldTensorProductConvLayer)
         if E == 0:   # models/tensor_layers.py:314-315: zeros, no BatchNorm, residual still applies
             out = torch.zeros((x.shape[0], self.out_size), dtype=torch.float32, device=x.device)
-            if self.residual:
+            if residual:
                 out[:, :x.shape[1]] += x
             return out.to(_dtype)
 
@@ -268,13 +280,17 @@ class TensorProductConvLayer(nn.Module):
             else:
                 prepared.append(None)
             s = e
-        return self._run(x, prepared, fcs, from_vec, ew_scalar, n_out, reduce, gather_scalars, scale, shift).to(_dtype)
+        return self._run(x, prepared, fcs, from_vec, ew_scalar, n_out, reduce, gather_scalars, scale, shift,
+                         residual=residual).to(_dtype)
 
     @torch.no_grad()
     def forward_groups(self, node_attr, groups, out_nodes=None, reduce='mean', gather_scalars=0):
         """Fast internal entry (used by diffdock_b200.CGModel): ``groups`` is a list with one item per radial MLP of this
-        layer, each ``(tgt_int32, src_int32, edge_attr, edge_vec, edge_weight | None)`` already CSR-sorted by target, so
-        that no per-layer concatenation / conversion / slicing of the edge arrays is needed."""
+        layer, each ``(tgt_int32, src_int32, edge_attr, edge_vec, edge_weight | None[, extras])`` already CSR-sorted by
+        target, so that no per-layer concatenation / conversion / slicing of the edge arrays is needed.  ``extras`` (dict)
+        carries the indirections of the fused kernel - ``n_edges_dev`` (live edge count in device memory, the arrays are
+        upper-bound buffers), ``edge_perm``, ``vec_sign``, ``ea_add`` / ``ea_add_idx`` (diffdock_b200/fused.py:fused_conv) -
+        and requires a layer shape the fused kernel supports."""
         x = node_attr.float()
         if x.stride(1) != 1:
             x = x.contiguous()
@@ -289,24 +305,41 @@ class TensorProductConvLayer(nn.Module):
             return out
         return self._run(x, prepared, fcs, True, 1.0, n_out, reduce, gather_scalars, scale, shift)
 
-    def _run(self, x, prepared, fcs, from_vec, ew_scalar, n_out, reduce, gather_scalars, scale, shift):
+    def fused_capable(self, k_edge, gather_scalars):
+        """True if every radial MLP of this layer runs on the fully fused kernel for ``k_edge`` per-edge attribute columns
+        (+ 2 x ``gather_scalars`` node scalars) with in-kernel spherical harmonics."""
+        if not self.tp.vec_capable:
+            return False
+        table = self.tp.table_vec
+        fcs = [self.fc] if self.edge_groups == 1 else list(self.fc)
+        k_in = k_edge + 2 * gather_scalars
+        return all(fused.ENABLED and self._fusable(fc, k_in) and fused.supported(table, fc[0].out_features, k_in) for fc in fcs)
+
+    def _run(self, x, prepared, fcs, from_vec, ew_scalar, n_out, reduce, gather_scalars, scale, shift, residual=None):
         handle = self.tp.handle(from_vec)
         table = handle.table
         sum_buf = torch.zeros((n_out, self.out_size), dtype=torch.float32, device=x.device)
         cnt_buf = torch.zeros((n_out,), dtype=torch.float32, device=x.device)
-        blk = max(1024, WEIGHT_BLOCK_BYTES // (4 * table.weight_numel_padded))
+        blk = None
         for item, fc in zip(prepared, fcs):
             if item is None:
                 continue
-            tgt32, src32, ea, geo, ew = item
+            tgt32, src32, ea, geo, ew = item[:5]
+            extras = item[5] if len(item) > 5 else None
             n_e = tgt32.shape[0]
             k_in = ea.shape[1] + 2 * gather_scalars
-            plan = self._fused_plan(fc, table, k_in) if (from_vec and ew_scalar == 1.0 and n_e >= 64) else None
+            plan = self._fused_plan(fc, table, k_in) \
+                if (from_vec and ew_scalar == 1.0 and (n_e >= 64 or extras is not None)) else None
             if plan is not None:      # radial MLP + tensor product + scatter in one kernel, no per-edge weights in HBM
-                fused.fused_conv(plan, ea.float(), x, gather_scalars, tgt32, src32, x, geo, sum_buf, cnt_buf,
-                                 edge_weight=ew)
+                fused.fused_conv(plan, ea.float(), x, gather_scalars, tgt32, src32, x, geo.float(), sum_buf, cnt_buf,
+                                 edge_weight=ew.float().contiguous() if ew is not None else None, **(extras or {}))
                 continue
+            if extras is not None:
+                raise RuntimeError("edge groups with device-side counts / indirections need a fused-kernel layer shape "
+                                   "(TensorProductConvLayer.fused_capable)")
             mlp_fused = self._fusable(fc, k_in) and n_e >= 64
+            if blk is None:
+                blk = _weight_block_edges(table.weight_numel_padded, x.device)
             if gather_scalars and not mlp_fused:     # library path needs the concatenated attributes
                 ea = torch.cat([ea, x[tgt32.long(), :gather_scalars], x[src32.long(), :gather_scalars]], -1)
             for b0 in range(0, n_e, blk):
@@ -321,7 +354,7 @@ class TensorProductConvLayer(nn.Module):
                 ops.tpconv_accumulate(handle, x, src32[b0:b1], tgt32[b0:b1], geo[b0:b1], w, sum_buf, cnt_buf,
                                       edge_weight=ew[b0:b1] if ew is not None else None, count_node_bytes=b0 == 0)
                 del w
-        res = x if self.residual else None
+        res = x if (self.residual if residual is None else residual) else None
         return ops.tpconv_finalize(sum_buf, cnt_buf, reduce == 'mean', scale, shift, res)
 
 
@@ -342,12 +375,10 @@ class OldTensorProductConvLayer(TensorProductConvLayer):
         if not self.residual:
             return super().forward(node_attr, edge_index, edge_attr, edge_sh, out_nodes, reduce, edge_weight,
                                    edge_vec=edge_vec, assume_sorted=assume_sorted, gather_scalars=gather_scalars)
-        bn, self.batch_norm, self.residual = self.batch_norm, None, False        # conv only, then residual -> BatchNorm
-        try:
-            out = super().forward(node_attr, edge_index, edge_attr, edge_sh, out_nodes, reduce, edge_weight,
-                                  edge_vec=edge_vec, assume_sorted=assume_sorted, gather_scalars=gather_scalars)
-        finally:
-            self.batch_norm, self.residual = bn, True
+        bn = self.batch_norm                                                      # conv only, then residual -> BatchNorm
+        out = super().forward(node_attr, edge_index, edge_attr, edge_sh, out_nodes, reduce, edge_weight,
+                              edge_vec=edge_vec, assume_sorted=assume_sorted, gather_scalars=gather_scalars,
+                              _conv_only=True)
         out = out + F.pad(node_attr, (0, out.shape[-1] - node_attr.shape[-1]))
         if bn is not None:
             scale, shift = bn.fold()

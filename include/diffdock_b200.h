@@ -114,6 +114,52 @@ int ddb200_pose_update(const float* pos, int64_t n_poses, int n_atoms, int n_bon
                        const float* rot_score, const float* tor_score, const float* tr_z, const float* rot_z,
                        const float* tor_z, const float* coef6, int use_torsion, float* out_pos, void* stream);
 
+/* Same update for a step loop that never returns to the host: the SDE coefficients come from row *step_dev (NULL = row 0)
+ * of a DEVICE table coef_table [n_steps, 6]; with pose_key != NULL the noise is drawn in-kernel from Philox4x32-10 keyed by
+ * (seed, pose_key[b] = (complex id << 32) | pose id) at counter (step, dof block) - the noise of a pose is then independent of
+ * batch composition and of the number of GPUs the poses are sharded over; otherwise tr_z / rot_z /
+ * tor_z (may be NULL) as above.  out_pos may alias pos. */
+int ddb200_pose_update_dev(const float* pos, int64_t n_poses, int n_atoms, int n_bonds, const int32_t* bond_u,
+                           const int32_t* bond_v, const uint8_t* mask_rotate, const float* tr_score,
+                           const float* rot_score, const float* tor_score, const float* tr_z, const float* rot_z,
+                           const float* tor_z, const float* coef_table, const int32_t* step_dev, uint64_t seed,
+                           const int64_t* pose_key, int use_torsion, float* out_pos, void* stream);
+/* Test hook: the four normals (and optionally the raw 4 x uint32 words) of Philox blocks block0 .. block0 + n_blocks - 1. */
+int ddb200_philox_probe(uint64_t seed, int64_t pose_key, uint32_t step, uint32_t block0, int n_blocks,
+                        float* out_normals, uint32_t* out_raw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Sync-free graph construction: fill pass that writes into caller-sized (upper-bound) buffers; the edge total stays in
+ * device memory (last element of the caller's inclusive scan) and is handed to the convolution as n_edges_dev.
+ *   row_start [n_y]   exclusive scan of (pre_ptr[q+1] - pre_ptr[q]) + radius count (ddb200_radius_count)
+ *   pre_ptr / pre_col optional CSR of static edges listed first for every query (the ligand bond edges of
+ *                     models/cg_model.py:478-483); out_eid [E] = index into pre_col, or -1 for radius edges
+ *   out_vec [E, 3]    x[col] - y[row]  (models/cg_model.py:491,508,552), optional
+ *   slot_out          optional dense table: slot_out[q * slot_ld + (i - x_ptr[b])] = edge position (forward pass of a
+ *                     bipartite graph);  slot_in / y_ptr / out_perm: reverse pass (queries and candidates swapped) emits
+ *                     out_perm[pos] = slot_in[i * slot_ld + (q - y_ptr[b])], the position of the same pair in the forward
+ *                     list, which ddb200_fused_conv takes as edge_perm (same pairs in both directions, :555-557).
+ *   row_offset / col_offset are added to the indices written to out_row / out_col (the model numbers ligand and receptor
+ *                     nodes jointly, models/cg_model.py:329-338).
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_graph_fill(const float* x, const float* y, const int32_t* x_ptr, const int32_t* y_batch,
+                      const float* r_per_graph, float r, int64_t n_y, int max_neighbors, int exclude_self,
+                      const int32_t* row_start, const int32_t* pre_ptr, const int32_t* pre_col, int32_t* out_row,
+                      int32_t* out_col, float* out_vec, int32_t* out_eid, int32_t* slot_out, const int32_t* slot_in,
+                      const int32_t* y_ptr, int slot_ld, int32_t* out_perm, int row_offset, int col_offset, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Ligand-receptor edge embedding, one kernel, live edge count on the device:
+ *   h = relu(u[edge_row[e]] + W1_rbf . rbf(|edge_vec[e]|)),  out[e] = W2 . h + b2,   rbf_k(d) = exp(coeff (d - offset_k)^2)
+ * u [n_rows, ns] = W1[:, :S] . sigma_emb + b1 per ligand node (the sigma-embedding half of the first Linear, computed once
+ * per node instead of once per edge); w1_rbf [ns, rbf_dim] = W1[:, S:]; w2 [ns, ns]; out [capacity, ns].
+ * Replaces: models/cg_model.py:553-554 (edge_attr = cat[sigma_emb, GaussianSmearing(d)]) + cross_edge_embedding at :326
+ * (models/layers.py:20-30 + Linear/ReLU/Linear).  Unsupported (rbf_dim, ns) -> DDB200_EINVAL.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_edge_embed(const float* edge_vec, const int32_t* edge_row, const float* u, const float* w1_rbf, const float* w2,
+                      const float* b2, int rbf_dim, int ns, const float* rbf_offset, float rbf_coeff, int64_t capacity,
+                      const int32_t* n_edges_dev, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Radial-MLP output layer on tcgen05 tensor cores:  out[e, n] = sum_k h[e, k] * W2[n, k] + bias[n], fp32-accurate
  * through a split-bf16 (hi/lo) product evaluated as one bf16 GEMM over K' = 3K.
@@ -143,20 +189,41 @@ int ddb200_radial_mlp(const float* edge_attr, int64_t ld_ea, int ne, const float
 /* ---------------------------------------------------------------------------------------------------------------
  * Fully fused convolution of one edge group: radial MLP (as ddb200_radial_mlp) whose output tiles are contracted with the
  * edge irreps straight out of tensor memory and scatter-added - the [E, weight_numel] weights never reach HBM.
- *   sum[tgt[e], :] += TP(x[src[e], :], Y(edge_vec[e]), FCBlock([edge_attr[e] | node[tgt[e],:ns] | node[src[e],:ns]])) * edge_weight[e]
+ *   r = edge_perm ? edge_perm[e] : e                                      (row of the per-edge input arrays)
+ *   a = [edge_attr[r] (+ ea_add[ea_add_idx[e]]) | node[tgt[e], :ns] | node[src[e], :ns]]
+ *   sum[tgt[e], :] += TP(x[src[e], :], Y(vec_sign * edge_vec[r]), FCBlock(a)) * edge_weight[r]
  *   cnt[tgt[e]]    += 1
- * w1_images / w2_images / tiles / ment / term_y / term_v: the plan built by diffdock_b200/fused.py (operand images with the
- * biases folded in, N tiles = whole rows of one path block, Clebsch-Gordan terms).  Supported shapes:
- * (mul_out, 2l_out+1) in {(48,1),(10,3),(16,1),(4,3)}, l_in <= 1, spherical harmonics from edge vectors (sh_lmax <= 2).
+ * for e < min(n_edges, *n_edges_dev): the edge count may live on the device (neighbour lists built without a host round
+ * trip); n_edges is then the capacity of the arrays.  edge_perm / vec_sign let one stored edge list serve both directions
+ * of a bipartite graph (the reverse direction reads the same attribute rows in another order with the vector negated,
+ * models/cg_model.py:556-557) and let poses share one copy of the static receptor edge attributes; ea_add carries the
+ * per-complex sigma-embedding term of models/cg_model.py:298-301 without materialising edge_attr + sigma per step.
+ * w1_images / w2_images / tiles / mtab: the plan built by diffdock_b200/fused.py (operand images [hi | lo | hi | bias] with
+ * 16-column-aligned sections, N tiles = whole rows of one path block, dense Clebsch-Gordan tables [path][3][3][5] padded to
+ * 48 floats).  Supported shapes: (mul_out, 2l_out+1) in {(48,1),(10,3),(16,1),(4,3)}, l_in <= 1, spherical harmonics from
+ * edge vectors (sh_lmax <= 2), ne + 2 ns <= 144, hidden <= 144.
  * Replaces: models/tensor_layers.py:139-144 / :204-221 including fc_layer(edge_attr) and the edge_attr_ assembly of
  * models/cg_model.py:342-349.  Follow with ddb200_tpconv_finalize.
  * ------------------------------------------------------------------------------------------------------------- */
-int ddb200_fused_conv(const float* edge_attr, int64_t ld_ea, int ne, const float* node, int64_t ld_node, int ns,
-                      const int32_t* tgt, const int32_t* src, const void* w1_images, int hidden, const void* w2_images,
-                      const int32_t* tiles, int n_tiles, const int32_t* ment, int n_ment, const int32_t* term_y,
-                      const float* term_v, int n_terms, const float* x, int64_t ld_x, const float* edge_vec,
-                      const float* edge_weight, int sh_lmax, int64_t n_edges, float* sum, int d_out, float* cnt,
-                      void* stream);
+typedef struct ddb200_fused_args {
+  const float*   edge_attr;   int64_t ld_ea;   int32_t ne;     /* [rows, ld_ea] per-edge attributes, ne columns used   */
+  const float*   node;        int64_t ld_node; int32_t ns;     /* node scalars of both end points (ns = 0: none)       */
+  const int32_t* tgt;         const int32_t* src;              /* [n_edges] scatter target / gathered node             */
+  const int32_t* edge_perm;                                    /* [n_edges] or NULL                                    */
+  const float*   ea_add;      const int32_t* ea_add_idx;       /* [*, ne] and [n_edges], both or neither               */
+  float          vec_sign;                                     /* +1 / -1 (0 is read as +1)                            */
+  const void*    w1_images;   int32_t hidden;
+  const void*    w2_images;
+  const int32_t* tiles;       int32_t n_tiles;                 /* [n_tiles][8]                                         */
+  const float*   mtab;        int32_t n_paths;                 /* [n_paths][48]                                        */
+  const float*   x;           int64_t ld_x;    int32_t x_pairs_ok;   /* x_pairs_ok: every tile offset / count is even  */
+  const float*   edge_vec;    const float* edge_weight;        /* [rows, 3]; [rows] or NULL                            */
+  int32_t        sh_lmax;
+  int64_t        n_edges;     const int32_t* n_edges_dev;      /* capacity (or count if n_edges_dev == NULL)           */
+  float*         sum;         int32_t d_out;   float* cnt;     /* [n_dst, d_out] fp32, [n_dst] fp32 or NULL            */
+} ddb200_fused_args;
+
+int ddb200_fused_conv(const ddb200_fused_args* args, void* stream);
 /* Execution: CTA pairs on tcgen05 cta_group::2 (256 edges per MMA, each CTA stages half of every weight image);
  * DDB200_FUSED_CTA_PAIR=0 selects the single-CTA kernel. */
 

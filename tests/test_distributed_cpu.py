@@ -38,7 +38,7 @@ def _worker(rank, world, port, n_poses, ret):
 
 
 def test_two_rank_sharded_sampling_gathers_all_poses():
-    for n_poses, port in ((5, 29611), (4, 29612)):     # uneven and even shards
+    for n_poses, port in ((5, 29611), (4, 29612), (1, 29613)):     # uneven, even, and an empty block on rank 1
         mgr = mp.Manager()
         ret = mgr.dict()
         mp.spawn(_worker, args=(2, port, n_poses, ret), nprocs=2, join=True)

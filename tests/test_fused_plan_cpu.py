@@ -1,6 +1,8 @@
 """Host logic of the fully fused convolution (diffdock_b200/fused.py): a numpy/torch emulation that reads ONLY the plan the
-kernel reads (swizzled bf16 operand images with folded biases, tile table, Clebsch-Gordan term tables) must reproduce
-the oracle layer.  Pins the image layout, the split-bf16 scheme and the tile/accumulator bookkeeping without a GPU."""
+kernel reads (swizzled bf16 operand images with folded biases, tile table, dense Clebsch-Gordan tables) and forms the
+products step by step like the kernel's MMA loop (16-column steps of the static operand paired with the activation image
+through the step map) must reproduce the oracle layer.  Pins the image layout, the split-bf16 scheme, the step map and the
+tile/accumulator bookkeeping without a GPU."""
 import math
 
 import pytest
@@ -22,14 +24,41 @@ def _deswizzle(img):
     return lin.permute(0, 2, 1, 3, 4).reshape(T, R, n_kb * 64).double()
 
 
-def _split_operand(a, kpad):
-    """fp32 activations [E, K] -> the kernel's A image [hi | hi | lo | 1 1 | 0...] as float64."""
+def _split_operand(a):
+    """fp32 activations [E, K] -> the kernel's A image [hi | lo | 1 1 0...] (sections padded to Kp) as float64."""
     hi = a.to(torch.bfloat16)
     lo = (a - hi.float()).to(torch.bfloat16)
     E, K = a.shape
-    out = torch.zeros(E, kpad, dtype=torch.float64)
-    out[:, :K], out[:, K:2 * K], out[:, 2 * K:3 * K] = hi.double(), hi.double(), lo.double()
-    out[:, 3 * K:3 * K + 2] = 1.0
+    Kp = (K + 15) // 16 * 16
+    out = torch.zeros(E, 2 * Kp + 16, dtype=torch.float64)
+    out[:, :K], out[:, Kp:Kp + K] = hi.double(), lo.double()
+    out[:, 2 * Kp:2 * Kp + 2] = 1.0
+    return out
+
+
+def _schedule(S, n_kb):
+    """csrc/fused_conv.cu:build_ops - (A column block, B column block) of every MMA, k-block by k-block."""
+    ops = []
+    for kb in range(n_kb):
+        for j in range(4):
+            c = 4 * kb + j
+            if c < S:
+                ops += [(c, c), (S + c, c)]          # B hi step x A hi, x A lo
+            elif c < 2 * S:
+                ops.append((c - S, c))               # B lo step x A hi
+            elif c == 2 * S:
+                ops.append((2 * S, c))               # bias step x ones
+    return ops
+
+
+def _mma(A, Bimg, K):
+    """A [E, 2Kp+16] x B [N, 2Kp+16 (+pad)]^T the way the kernel issues it: one 16-column MMA step at a time."""
+    S = (K + 15) // 16
+    out = torch.zeros(A.shape[0], Bimg.shape[0], dtype=torch.float64)
+    ops = _schedule(S, Bimg.shape[1] // 64)
+    assert len(ops) == 3 * S + 1
+    for a, b in ops:
+        out += A[:, 16 * a:16 * a + 16] @ Bimg[:, 16 * b:16 * b + 16].T
     return out
 
 
@@ -44,32 +73,32 @@ def _sh(vec):
 def emulate(plan, ea, node, ns, tgt, src, x, vec, n_out, ew=None):
     E = ea.shape[0]
     a0 = torch.cat([ea, node[tgt, :ns], node[src, :ns]], 1) if ns else ea
-    n_kb1, n_kb = plan.w1_images.shape[1], plan.w2_images.shape[1]
     w1 = _deswizzle(plan.w1_images)[0]                                   # [256, K1']
     H = plan.hidden
-    hid = torch.relu(_split_operand(a0, n_kb1 * 64) @ w1[:H].T).float()  # fp32 accumulator -> ReLU
-    A = _split_operand(hid, n_kb * 64)
+    hid = torch.relu(_mma(_split_operand(a0), w1[:H], a0.shape[1])).float()      # fp32 accumulator -> ReLU
+    A = _split_operand(hid)
     w2 = _deswizzle(plan.w2_images)                                      # [T, 256, K']
     Y = _sh(vec)
-    tiles, ment = plan.tiles.tolist(), plan.ment.reshape(-1, 2).tolist()
-    ty, tv = plan.term_y.tolist(), plan.term_v.double()
+    tiles = plan.tiles.tolist()
+    mtab = plan.mtab.double()[:, :45].reshape(-1, 3, 3, 5)               # [path][i][k][j]
     out = torch.zeros(n_out, plan.table.d_out, dtype=torch.float64)
     acc = None
-    for t, (kind, n_mma, x_off, nrow, d_in, out_off, flags, ment_off) in enumerate(tiles):
+    for t, (kind, n_mma, x_off, nrow, d_in, out_off, flags, path) in enumerate(tiles):
         mul_out, dout, rows = KINDS[kind]
-        assert n_mma == mul_out * rows and n_mma % 16 == 0 and n_mma <= 192
-        Wt = A @ w2[t, :n_mma].T                                         # [E, N]: the TMEM accumulator tile
-        M = torch.zeros(E, 3, 3, dtype=torch.float64)
-        for i in range(d_in):
-            for k in range(dout):
-                b, n = ment[ment_off + i * dout + k]
-                for q in range(b, b + n):
-                    M[:, i, k] += tv[q] * Y[:, ty[q]]
+        assert n_mma % 32 == 0 and nrow * mul_out <= n_mma <= mul_out * rows <= 192
+        Wt = torch.zeros(E, mul_out * rows, dtype=torch.float64)         # columns beyond n_mma are never produced
+        Wt[:, :n_mma] = _mma(A, w2[t, :n_mma], H)                        # [E, N]: the TMEM accumulator tile
+        sh_off = (flags >> 8) & 0xff
+        yb = torch.zeros(E, 5, dtype=torch.float64)
+        for j in range(5):
+            yb[:, j] = Y[:, min(sh_off + j, 8)]
+        M = torch.einsum('ikj,ej->eik', mtab[path], yb)
         if ew is not None:
             M = M * ew.double().reshape(-1, 1, 1)
         xs = torch.zeros(E, rows, d_in, dtype=torch.float64)
         xs[:, :nrow] = x[src][:, x_off:x_off + nrow * d_in].double().reshape(E, nrow, d_in)
         z = torch.einsum('eri,eik->erk', xs, M[:, :d_in, :dout])         # [E, rows, dout]
+        z[:, (n_mma // mul_out) + (1 if n_mma % mul_out else 0):] = 0   # rows whose columns lie beyond the MMA width
         if flags & 1:
             acc = torch.zeros(E, mul_out, dout, dtype=torch.float64)
         acc = acc + torch.einsum('erw,erk->ewk', Wt.reshape(E, rows, mul_out), z)
@@ -127,9 +156,11 @@ def test_fused_plan_tile_flags_and_limits():
     seen_out = []
     for i, (kind, n, x_off, nrow, d_in, out_off, flags, ment) in enumerate(tiles):
         mul_out, dout, rows = KINDS[kind]
-        assert n == mul_out * rows and n % 16 == 0 and 16 <= n <= 192 and (n // 2) % 8 == 0
+        assert nrow * mul_out <= n <= mul_out * rows and n % 32 == 0 and 32 <= n <= 192 and (n // 2) % 8 == 0
+        assert (flags >> 8) in (0, 1, 4)            # offset of the path's l_sh block in the spherical-harmonics vector
         assert 1 <= nrow <= rows and d_in in (1, 3) and 0 <= x_off and x_off + nrow * d_in <= table.d_in
         assert out_off + mul_out * dout <= table.d_out
+        flags &= 0xff
         if flags & 1:
             assert out_off not in seen_out, "tiles of one output irrep must be contiguous"
             seen_out.append(out_off)

@@ -63,8 +63,10 @@ if __name__ == '__main__':
     r = {'E': E, 'tiles': plan.n_tiles, 'ms': round(ms, 3), 'bf16_issued_TFLOPs': round(flops / ms / 1e9, 1),
          'pair': os.environ.get('DDB200_FUSED_CTA_PAIR', '1')}
     if have_dbg and _lib.lib().ddb200_fused_debug_read(dbg) == 0:
-        units = max(int(dbg[12]), 1)
-        r['clk_per_unit'] = {NAMES[i]: int(dbg[i]) // units for i in NAMES if i != 12}
+        pair = os.environ.get('DDB200_FUSED_CTA_PAIR', '1') != '0'
+        units = max(int(dbg[12]), 1)         # counted once per CTA: a pair unit counts twice
+        one_cta = {0, 1, 2, 3, 6, 7}         # counters only the leader (MMA role) or only the peer (relay) adds to
+        r['clk_per_cta_unit'] = {NAMES[i]: int(dbg[i]) * (2 if (pair and i in one_cta) else 1) // units for i in NAMES if i != 12}
         r['units'] = units // 5
         r['issue_clk_per_mma'] = round(dbg[13] / max(dbg[14], 1), 1)
     print(json.dumps(r), flush=True)
