@@ -6,10 +6,14 @@
 
 A "step" is one reverse-diffusion step of the hot path for one batch: set_time -> score-model forward (graph build,
 embeddings, 6 tensor-product conv layers, tr/rot/tor heads) -> pose update, for POSES poses of one synthetic complex
-(1500 residues / 40 ligand atoms, BASELINE config 2) per GPU; consecutive steps walk the 20-step 'expbeta' schedule
-(t: 1 -> 0.05), so K=20 is exactly one sampling run.   value = total poses / (20 * mean step time).
-The JSON line also carries the end-to-end number through diffdock_b200.sampling.sampling() with host inputs, the
-HBM roofline of the fused tensor-product conv kernel measured live with CUDA events, and a CPU baseline.
+(1500 residues / 40 ligand atoms; 40 poses = BASELINE config 3, the full sampling loop) per GPU; consecutive steps walk
+the 20-step 'expbeta' schedule (t: 1 -> 0.05), so K=20 is exactly one sampling run.  value = total poses / (20 * mean step
+time), steps launched as replays of the sampler's CUDA graph (diffdock_b200.sampling.GraphedSteps), inputs resident.
+The JSON line also carries: the end-to-end number through diffdock_b200.sampling.sampling() with host inputs (median of 3
+calls after one warm call), the same measurement for BASELINE config 2 (batch 32) and for the sh_lmax=1 model (CFG-L1), the
+roofline of the fused tensor-product conv kernel on ALGORITHMIC work (SURVEY 8(d) bytes and fp32 FLOPs per edge) next to
+the issued tensor-pipe rate, measured live with CUDA events, the parity of the timed workload against the CPU oracle, and
+the CPU baseline.
 """
 from __future__ import annotations
 
@@ -97,9 +101,10 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------- CPU oracle arm
-def oracle_step_fn(args, n_res, n_atoms, seed):
+def oracle_step_fn(args, n_res, n_atoms, seed, want_scores=False):
     """One bounded sample of the workload on the host: ONE pose of the same synthetic complex - score-model forward
-    (oracle restatement of the reference's e3nn/torch_scatter op sequence) + pose update, at schedule point t_idx."""
+    (oracle restatement of the reference's e3nn/torch_scatter op sequence) + the SDE perturbation WITH its noise terms +
+    pose update, at schedule point t_idx (utils/sampling.py:96-191).  The pose returns to the prior at t_idx == 0."""
     from oracle.cg_model import CGModel
     from oracle.diffusion import modify_conformer_batch, set_time, t_to_sigma
     from oracle.layers import get_timestep_embedding
@@ -111,19 +116,48 @@ def oracle_step_fn(args, n_res, n_atoms, seed):
     randomise_bn(model, 1)
     pose = make_pose_list(1, n_res=n_res, n_atoms=n_atoms, seed=seed, tr_sigma_max=args.tr_sigma_max)
     g = collate(pose)
+    pos0 = g['ligand'].pos.clone()
     sched = get_t_schedule('expbeta', N_SCHED)
     mask_rotate = torch.from_numpy(pose[0]['ligand'].mask_rotate[0])
+    gen = torch.Generator().manual_seed(7)
 
-    def step(i):
-        t_idx = i % N_SCHED
+    def step(t_idx, pos=None):
+        t_idx = t_idx % N_SCHED
+        if pos is not None:
+            g['ligand'].pos = pos.clone()
+        elif t_idx == 0:
+            g['ligand'].pos = pos0.clone()
         t = sched[t_idx]
         set_time(g, t, t, t, 1, 'cpu')
         with torch.no_grad():
             tr, rot, tor, _ = model(g)
             c = step_coefficients(t_idx, N_SCHED, sched, sched, sched, partial(t_to_sigma, args=args), args, False,
                                   **TEMPS)
-            g['ligand'].pos = modify_conformer_batch(g['ligand'].pos, g, c[0] * tr, c[2] * rot, c[4] * tor, mask_rotate)
+            last = t_idx == N_SCHED - 1
+            z = (lambda shape: torch.zeros(shape)) if last else (lambda shape: torch.randn(shape, generator=gen))
+            g['ligand'].pos = modify_conformer_batch(g['ligand'].pos, g, c[0] * tr + c[1] * z(tr.shape),
+                                                     c[2] * rot + c[3] * z(rot.shape), c[4] * tor + c[5] * z(tor.shape),
+                                                     mask_rotate)
+        return (tr, rot, tor) if want_scores else None
+    step.pos0, step.model, step.graph = pos0, model, g
     return step
+
+
+# schedule points the CPU arm times when the whole 20-step trajectory does not fit its budget: both ends and three interior
+# points; the per-step cost falls monotonically with t (the cross graph shrinks with 3 sigma_tr + 20 A), so the trapezoid
+# rule over these points estimates the trajectory total without the high-noise bias of "the first few steps".
+STRATA = (0, 5, 10, 15, 19)
+
+
+def trajectory_seconds(costs):
+    """costs: {t_idx: seconds}.  Sum over t_idx = 0..19 of the piecewise-linear interpolant through the measured points."""
+    pts = sorted(costs)
+    if len(pts) == N_SCHED:
+        return float(sum(costs.values()))
+    if len(pts) == 1:
+        return float(N_SCHED * costs[pts[0]])
+    xs = np.arange(N_SCHED)
+    return float(np.interp(xs, pts, [costs[p] for p in pts]).sum())
 
 
 def run_reference(cli):
@@ -134,38 +168,54 @@ def run_reference(cli):
     torch.set_num_threads(cores)
     args = default_model_args(sh_lmax=cli.sh_lmax)
     step = oracle_step_fn(args, cli.n_res, cli.n_atoms, seed=100)
-    budget = float(os.environ.get('DDB200_REF_BUDGET_S', '240'))
+    budget = float(os.environ.get('DDB200_REF_BUDGET_S', '300'))
     t0 = time.perf_counter()
-    step(0)                       # first warm-up step doubles as the cost probe
+    step(N_SCHED - 1)             # warm-up at the cheapest schedule point doubles as the cost probe
     probe = time.perf_counter() - t0
-    warm = max(0, min(cli.warmup, int(budget * 0.2 / max(probe, 1e-3))) - 1)
-    for i in range(warm):
-        step(1 + i)
-    steps = max(1, min(cli.steps, int((budget - probe * (1 + warm)) / max(probe, 1e-3))))
-    t0 = time.perf_counter()
-    for i in range(steps):
-        step(1 + warm + i)
-    dt = (time.perf_counter() - t0) / steps
-    value = 1.0 / (N_SCHED * dt)
-    sample = (f"1 pose of the {cli.n_res}-residue/{cli.n_atoms}-atom complex per step (forward + pose update); "
-              f"{steps} of the requested {cli.steps} steps timed within a {budget:.0f} s budget")
+    warm = 1
+    # cost at t_idx 0 is ~2.5-3.5x the probe (measured: 40 s vs 12-16 s); the trajectory averages ~1.7x
+    if cli.steps >= N_SCHED and probe * (1.7 * N_SCHED + max(cli.warmup - 1, 0)) <= budget:
+        points = list(range(N_SCHED))
+        for _ in range(max(cli.warmup - 1, 0)):
+            step(N_SCHED - 1)
+            warm += 1
+    else:
+        k = min(len(STRATA), cli.steps)
+        points = list(STRATA) if k >= len(STRATA) else ([0, N_SCHED - 1] if k >= 2 else [N_SCHED // 2])
+    costs = {}
+    for t_idx in points:          # in schedule order (the cost of a step is set by its cut-off 3 sigma_tr(t) + 20 A)
+        t0 = time.perf_counter()
+        step(t_idx)
+        costs[t_idx] = time.perf_counter() - t0
+    total = trajectory_seconds(costs)
+    steps = len(points)
+    value = 1.0 / total           # one pose through the full 20-step schedule
+    sample = (f"1 pose of the {cli.n_res}-residue/{cli.n_atoms}-atom complex per step (forward + noise + pose update); "
+              f"schedule points {points} timed ({', '.join(f'{costs[p]:.1f}' for p in points)} s), trajectory total "
+              f"{'summed' if steps == N_SCHED else 'by trapezoid interpolation over the 20 points'} = {total:.0f} s; "
+              f"budget {budget:.0f} s")
     line = {"impl": "reference", "metric": "poses/sec at 20 diffusion steps", "value": value, "unit": "poses/s",
-            "n_gpus": cli.gpus, "steps": steps, "warmup": 1 + warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "n_gpus": cli.gpus, "steps": steps, "warmup": warm, "ms_per_step": total / N_SCHED * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cli, cli.poses),      # same workload as the CUDA arm; the bounded sample is below
+            "schedule_points": points, "seconds_per_point": {str(k): v for k, v in costs.items()},
             "cpu_baseline": {"value": value, "unit": "poses/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(cli, poses):
+    cfgname = "BASELINE config 3 (full 20-step sampling loop, 40 poses/complex)" if poses == 40 else \
+        ("BASELINE config 2 (batch 32)" if poses == 32 else f"{poses} poses")
     return {"workload": f"DiffDock-L-shaped score model (ns=48,nv=10,sh_lmax={cli.sh_lmax},6 conv layers) reverse-diffusion "
                         f"step, synthetic complex {cli.n_res} residues / {cli.n_atoms} ligand atoms, {poses} poses per GPU "
-                        f"(BASELINE config 2), 20-step expbeta schedule",
+                        f"[{cfgname}], 20-step expbeta schedule",
             "poses_per_gpu": poses, "n_res": cli.n_res, "n_atoms": cli.n_atoms, "sh_lmax": cli.sh_lmax,
             "l2": "per-step working set (edge embeddings ~0.3 GB per receptor edge group and layer, operand images, "
                   "node tensors) exceeds the 126 MB L2; no explicit flush",
             "warmup_executed": cli.warmup if getattr(cli, 'short_warmup', False) else max(cli.warmup, N_SCHED),
+            "launch": "one CUDA-graph replay per step (diffdock_b200.sampling.GraphedSteps); the eager op-by-op step is "
+                      "reported as eager_ms_per_step",
             "parallelism": f"poses sharded over {cli.gpus} GPU(s), no data-path collective"}
 
 
@@ -208,12 +258,115 @@ def tpconv_stream_roofline(dev, n_edges=200000):
                    "fused kernel (see 'roofline')"}
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch of the fused kernel from the committed ncu capture of this round (None if absent): the run
+    itself cannot read dram__bytes without a profiler attached."""
+    p = os.path.join(ROOT, 'profiles', 'r02_fused_traffic.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class Workload:
+    """Model + one batch of POSES poses of the synthetic complex on this rank's GPU, with the three ways of running it:
+    graph replays (the timed region), eager steps (per-launch events for the roofline), sampling() from host inputs (e2e)."""
+
+    def __init__(self, cli, n_poses, sh_lmax, dev, rank, seed=None):
+        from diffdock_b200.cg_model import CGModel
+        from diffdock_b200.diffusion_utils import get_t_schedule, get_timestep_embedding, t_to_sigma
+        from diffdock_b200.sampling import GraphedSteps, step_coefficients
+        self.cli, self.n_poses, self.dev = cli, n_poses, dev
+        self.args = args = default_model_args(sh_lmax=sh_lmax)
+        self.t2s = partial(t_to_sigma, args=args)
+        torch.manual_seed(0)
+        model = CGModel(self.t2s, dev, get_timestep_embedding('sinusoidal', args.sigma_embed_dim, args.embedding_scale),
+                        **model_kwargs(args)).eval()
+        randomise_bn(model, 1)
+        self.model = model.to(dev)
+        self.poses = make_pose_list(n_poses, n_res=cli.n_res, n_atoms=cli.n_atoms, seed=(100 + rank) if seed is None else seed,
+                                    tr_sigma_max=args.tr_sigma_max)
+        self.sched = get_t_schedule('expbeta', N_SCHED)
+        lig0 = self.poses[0]['ligand']
+        self.mask_u8 = torch.from_numpy(lig0.mask_rotate[0].astype(np.uint8)).to(dev)
+        rb = self.poses[0]['ligand', 'ligand'].edge_index.T[lig0.edge_mask]
+        self.bu, self.bv = rb[:, 0].int().contiguous().to(dev), rb[:, 1].int().contiguous().to(dev)
+        self.g = collate(self.poses).to(dev)
+        self.pos0 = self.g['ligand'].pos.clone()
+        self.coef_rows, self.t_rows = [], []
+        for t_idx in range(N_SCHED):
+            c = step_coefficients(t_idx, N_SCHED, self.sched, self.sched, self.sched, self.t2s, args, False, **TEMPS)
+            if t_idx == N_SCHED - 1:
+                c[1] = c[3] = c[5] = 0.0
+            self.coef_rows.append(c)
+            self.t_rows.append([float(self.sched[t_idx])] * 3)
+        self.graphed = None
+        if model.sync_free_capable() and os.environ.get('DDB200_CUDA_GRAPH', '1') != '0':
+            self.graphed = GraphedSteps(self.model, self.g, n_poses, self.coef_rows, self.t_rows, self.bu, self.bv, self.mask_u8,
+                                        True, dev, draw_noise=True, philox=(1234 + rank, torch.arange(n_poses, device=dev)))
+            self.pos0 = self.graphed.pos.clone()
+        self.gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def graph_step(self, i):
+        t_idx = i % N_SCHED
+        if t_idx == 0:            # a fresh sampling run starts from the prior again
+            self.graphed.pos.copy_(self.pos0)
+            self.graphed.step.zero_()
+        self.graphed.graph.replay()
+
+    def eager_step(self, i):
+        from diffdock_b200 import ops
+        from diffdock_b200.diffusion_utils import set_time
+        g, dev, n = self.g, self.dev, self.n_poses
+        t_idx = i % N_SCHED
+        if t_idx == 0:
+            g['ligand'].pos = self.pos0.clone()
+        t = self.sched[t_idx]
+        set_time(g, None, t, t, t, n, False, dev)
+        tr, rot, tor = self.model(g)[:3]
+        last = t_idx == N_SCHED - 1
+        z = (lambda shape: None) if last else (lambda shape: torch.randn(shape, device=dev, generator=self.gen))
+        g['ligand'].pos = ops.pose_update(g['ligand'].pos, n, self.bu, self.bv, self.mask_u8, tr, rot, tor,
+                                          self.coef_rows[t_idx], z((n, 3)), z((n, 3)), z(tuple(tor.shape)))
+
+    def step(self, i):
+        (self.graph_step if self.graphed is not None else self.eager_step)(i)
+
+    def e2e(self, host_list, repeats=3):
+        """sampling() from pinned host inputs to host outputs: median wall time of `repeats` calls after one warm call."""
+        from diffdock_b200.sampling import sampling
+        times, final = [], None
+        for r in range(repeats + 1):
+            inp = [p.clone() for p in host_list]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out, _ = sampling(inp, self.model, N_SCHED, self.sched, self.sched, self.sched, self.dev, self.t2s, self.args,
+                              batch_size=self.n_poses, no_final_step_noise=True, **TEMPS)
+            final = torch.stack([d['ligand'].pos for d in out]).cpu()      # D2H of the result inside the timed region
+            torch.cuda.synchronize()
+            if r > 0:
+                times.append(time.perf_counter() - t0)
+        return sorted(times)[len(times) // 2], times, final
+
+
+def timed_steps(w, steps, warmup_steps, sync_all):
+    for i in range(warmup_steps):
+        w.step(i)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        w.step(warmup_steps + i)
+    e1.record()
+    sync_all()
+    return e0.elapsed_time(e1) / steps
+
+
 def run_cuda(cli):
     import torch.distributed as dist
     from diffdock_b200 import ops
-    from diffdock_b200.cg_model import CGModel
-    from diffdock_b200.diffusion_utils import get_t_schedule, get_timestep_embedding, set_time, t_to_sigma
-    from diffdock_b200.sampling import sampling, step_coefficients
     import __graft_entry__ as ge
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -226,35 +379,6 @@ def run_cuda(cli):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
         dist.barrier()
-    args = default_model_args(sh_lmax=cli.sh_lmax)
-    t2s = partial(t_to_sigma, args=args)
-    torch.manual_seed(0)
-    model = CGModel(t2s, dev, get_timestep_embedding('sinusoidal', args.sigma_embed_dim, args.embedding_scale),
-                    **model_kwargs(args)).eval()
-    randomise_bn(model, 1)
-    model = model.to(dev)
-    poses = make_pose_list(cli.poses, n_res=cli.n_res, n_atoms=cli.n_atoms, seed=100 + rank, tr_sigma_max=args.tr_sigma_max)
-    sched = get_t_schedule('expbeta', N_SCHED)
-    lig0 = poses[0]['ligand']
-    mask_u8 = torch.from_numpy(lig0.mask_rotate[0].astype(np.uint8)).to(dev)
-    rb = poses[0]['ligand', 'ligand'].edge_index.T[lig0.edge_mask]
-    bu, bv = rb[:, 0].int().contiguous().to(dev), rb[:, 1].int().contiguous().to(dev)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    g = collate(poses).to(dev)
-    pos0 = g['ligand'].pos.clone()
-
-    def step(i):
-        t_idx = i % N_SCHED
-        if t_idx == 0:
-            g['ligand'].pos = pos0.clone()       # a fresh sampling run starts from the prior again
-        t = sched[t_idx]
-        coef = step_coefficients(t_idx, N_SCHED, sched, sched, sched, t2s, args, False, **TEMPS)
-        set_time(g, None, t, t, t, cli.poses, False, dev)
-        tr, rot, tor = model(g)[:3]
-        last = t_idx == N_SCHED - 1
-        z = (lambda shape: None) if last else (lambda shape: torch.randn(shape, device=dev, generator=gen))
-        g['ligand'].pos = ops.pose_update(g['ligand'].pos, cli.poses, bu, bv, mask_u8, tr, rot, tor, coef,
-                                          z((cli.poses, 3)), z((cli.poses, 3)), z(tuple(tor.shape)))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -262,99 +386,125 @@ def run_cuda(cli):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # Warm-up: the W requested steps, extended to one full pass over the 20-point schedule: every step of the schedule
-    # has its own neighbour-list sizes, and the first visit of each grows torch's caching allocator (cudaMalloc + sync).
-    # Measured: 67.0 ms/step when only steps 0-2 were warmed, 57.4 ms/step on the second pass over the same steps.
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ops.PROFILE.reset(enabled=False)
+    w = Workload(cli, cli.poses, cli.sh_lmax, dev, rank)
+    launches_per_step = None
+    # Warm-up: the W requested steps, extended to one full pass over the 20-point schedule (every point of the schedule
+    # has its own neighbour-list sizes; the graph replays have static shapes, the eager path grows the allocator).
     n_warm = cli.warmup if cli.short_warmup else max(cli.warmup, N_SCHED)
-    for i in range(n_warm):
-        step(i + cli.warmup - n_warm)
-    sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(n_warm):
+        w.step(i + cli.warmup - n_warm)
+    sync_all()
     if sampler:
         sampler.start()
     ops.PROFILE.reset(enabled=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(cli.steps):
-        step(cli.warmup + i)
+        w.step(cli.warmup + i)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1) / cli.steps
-    launches = ops.PROFILE.all_launches
     clocks = sampler.stop() if sampler else None
-    # Per-kernel durations: the SAME K steps replayed with a CUDA-event pair (launching stream) around every
-    # tensor-product conv launch, kept out of the timed region (its own step time is reported as replay_ms_per_step).
-    ops.PROFILE.reset(enabled=True)
+    ms_max = max_over_ranks(ms)
+    value = world * cli.poses / (N_SCHED * ms_max * 1e-3)
+
+    # Per-kernel durations: K EAGER steps with a CUDA-event pair (launching stream) around every tensor-product conv launch,
+    # kept out of the timed region; the same kernels as the graph replays, launched one by one.
+    for i in range(3):
+        w.eager_step(i)
+    torch.cuda.synchronize()
+    ops.PROFILE.reset(enabled=False)
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     r0.record()
     for i in range(cli.steps):
-        step(cli.warmup + i)
+        w.eager_step(cli.warmup + i)
     r1.record()
+    torch.cuda.synchronize()
+    eager_ms = r0.elapsed_time(r1) / cli.steps
+    launches_per_step = ops.PROFILE.all_launches / cli.steps
+    ops.PROFILE.reset(enabled=True)
+    for i in range(cli.steps):
+        w.eager_step(cli.warmup + i)
     prof = ops.PROFILE.summary()
-    prof['all_launches'] = launches
-    prof['replay_ms_per_step'] = r0.elapsed_time(r1) / cli.steps
     ops.PROFILE.reset(enabled=False)
-    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    value = world * cli.poses / (N_SCHED * ms_max * 1e-3)
 
-    # ---- end to end through the public API with host inputs ---------------------------------------------------
     if cli.no_e2e:
         if rank == 0:
-            print(json.dumps({"profiling_run": True, "ms_per_step": ms_max, "value": value, "tpconv": prof}), flush=True)
+            print(json.dumps({"profiling_run": True, "ms_per_step": ms_max, "value": value, "eager_ms_per_step": eager_ms,
+                              "tpconv": prof}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
-    host_list = [p.clone() for p in poses]
+
+    # ---- end to end through the public API with host inputs ---------------------------------------------------
+    host_list = [p.clone() for p in w.poses]
     for p in host_list:
         p._apply(lambda t: t.pin_memory() if t.is_floating_point() or t.dtype in (torch.int64, torch.bool) else t)
-    h2d = sum(t.numel() * t.element_size() for p in host_list for st in list(p._nodes.values()) + list(p._edges.values())
-              for t in st.__dict__.values() if torch.is_tensor(t))
+    h2d_unique = sum(t.numel() * t.element_size() for st in list(host_list[0]._nodes.values()) + list(host_list[0]._edges.values())
+                     for t in st.__dict__.values() if torch.is_tensor(t))
+    lig_bytes = sum(t.numel() * t.element_size() for k, st in list(host_list[0]._nodes.items()) + list(host_list[0]._edges.items())
+                    if 'receptor' not in k for t in st.__dict__.values() if torch.is_tensor(t))
+    h2d = h2d_unique + (cli.poses - 1) * lig_bytes          # one receptor copy + every pose's ligand (shared-receptor collate)
     sync_all()
-    t0 = time.perf_counter()
-    out, _ = sampling(host_list, model, N_SCHED, sched, sched, sched, dev, t2s, args, batch_size=cli.poses,
-                      no_final_step_noise=True, **TEMPS)
-    final = torch.stack([d['ligand'].pos for d in out]).cpu()        # D2H of the result inside the timed region
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        gathered = [torch.empty_like(final, device=dev) for _ in range(world)]   # final pose gather over NCCL
+    e2e_s, e2e_all, final = w.e2e(host_list)
+    e2e_max = max_over_ranks(e2e_s)
+    if world > 1:       # final pose gather over NCCL
+        gathered = [torch.empty_like(final, device=dev) for _ in range(world)]
         dist.all_gather(gathered, final.to(dev))
-    e2e_val = world * cli.poses / float(t_e.item())
+    e2e_val = world * cli.poses / e2e_max
     assert torch.isfinite(final).all()
+
+    extra = {}
+    if rank == 0 and world == 1 and not cli.quick:
+        # BASELINE config 2 (batch 32) and CFG-L1 (sh_lmax = 1: FasterTensorProduct weight layout) on the same complex
+        for key, poses, lmax in (("config2_batch32", 32, cli.sh_lmax), ("cfg_l1_sh_lmax1", cli.poses, 1)):
+            if poses == cli.poses and lmax == cli.sh_lmax:
+                continue
+            w2 = Workload(cli, poses, lmax, dev, rank)
+            ms2 = timed_steps(w2, N_SCHED, N_SCHED, sync_all)
+            hl = [p.clone() for p in w2.poses]
+            s2, _, _ = w2.e2e(hl, repeats=1)
+            extra[key] = {"value": poses / (N_SCHED * ms2 * 1e-3), "unit": "poses/s", "ms_per_step": ms2, "poses": poses,
+                          "sh_lmax": lmax, "e2e_value": poses / s2, "graphed": w2.graphed is not None}
+            del w2
+            torch.cuda.empty_cache()
 
     stream_roof = tpconv_stream_roofline(dev) if rank == 0 else None
     if rank == 0:
         pk, pk_kind = peaks()
         roof = None
         if prof['fused_launches']:
-            ach = prof['fused_flops'] / (prof['fused_ms'] * 1e-3) / 1e12
+            sec = prof['fused_ms'] * 1e-3
+            issued = prof['fused_flops'] / sec / 1e12
+            alg = prof['fused_alg_flops'] / sec / 1e12
+            eq_gbs = prof['fused_bytes'] / sec / 1e9
             peak_tf = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
-            roof = {"bound": "tensor", "kernel": "fused_conv_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "peak_kind": pk_kind + " (sustained bf16 cuBLAS: kernel timed inside a long step)",
-                    "traffic": None,
-                    "traffic_ncu": {"dram_bytes_per_launch": 151.7e6, "edges_per_launch": 400000,
-                                    "source": "profiles/r01i_fused_summary.csv (tools/bench_fused.py under ncu --set full); "
-                                              "the un-fused formulation moves 11.4 GB for the same launch"},
+            ncu = _ncu_traffic()
+            roof = {"bound": "hbm", "kernel": "fused_conv_kernel",
+                    "achieved": eq_gbs, "peak": pk['hbm_gbs'], "unit": "GB/s", "frac": eq_gbs / pk['hbm_gbs'],
+                    "peak_kind": pk_kind + " (HBM copy bandwidth, MEASURED_PEAKS.json)",
+                    "definition": "SURVEY 8(d): ALGORITHMIC bytes of the tensor-product convolution (E (4 W + 16) + node "
+                                  "tensors; the per-edge weights W counted as an HBM stream although the fused kernel keeps "
+                                  "them in tensor memory) / fused-kernel time; may exceed 1 because of that",
+                    "traffic": (ncu or {}).get('dram_bytes_per_launch'), "traffic_source": (ncu or {}).get('source'),
+                    "tensor": {"issued_TFLOPs": issued, "issued_frac_of_bf16_peak": issued / peak_tf, "bf16_peak_TFLOPs": peak_tf,
+                               "algorithmic_TFLOPs": alg,
+                               "algorithmic_def": "fp32 FLOPs of the reference formulation per edge: radial MLP 2 K H + 2 H W "
+                                                  "and the tensor product (SURVEY 8(d)); issued = bf16 tcgen05 FLOPs (split-bf16 "
+                                                  "x3 + bias step, 16-column K steps, N tiles trimmed to 32 columns)",
+                               "issued_over_algorithmic": issued / alg if alg else None},
                     "launches": prof['fused_launches'],
-                    "timing": "CUDA-event pair per launch on the launching stream, over a replay of the timed K steps "
-                              "(the timed region itself carries no per-launch events)",
-                    "replay_ms_per_step": prof['replay_ms_per_step'],
-                    "flops": "bf16 tcgen05 MMA FLOPs issued (radial MLP as split-bf16 x3, K padded to 448, full N tiles)",
-                    "kernel_ms_per_step": prof['fused_ms'] / cli.steps, "share_of_step": prof['fused_ms'] / cli.steps / ms,
-                    "equivalent_hbm_GBps": prof['fused_bytes'] / (prof['fused_ms'] * 1e-3) / 1e9,
-                    "equivalent_note": "algorithmic bytes of the un-fused formulation (SURVEY 8(d)) / fused-kernel time; "
-                                       "the per-edge weights never reach HBM, so this may exceed the HBM peak"}
-        elif prof['launches']:
-            ach = prof['bytes'] / (prof['ms'] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "tpconv_accumulate_kernel", "achieved": ach, "peak": pk['hbm_gbs'],
-                    "unit": "GB/s", "frac": ach / pk['hbm_gbs'], "peak_kind": pk_kind, "traffic": None,
-                    "launches": prof['launches'], "kernel_ms_per_step": prof['ms'] / cli.steps,
-                    "share_of_step": prof['ms'] / cli.steps / ms}
+                    "timing": "CUDA-event pair per launch on the launching stream, over K eager steps after the timed region "
+                              "(the timed region replays CUDA graphs and carries no per-launch events)",
+                    "kernel_ms_per_step": prof['fused_ms'] / cli.steps, "share_of_step": prof['fused_ms'] / cli.steps / ms}
         if stream_roof:
             stream_roof.update(peak=pk['hbm_gbs'], frac=stream_roof['achieved'] / pk['hbm_gbs'], peak_kind=pk_kind)
         line = {"metric": "poses/sec at 20 diffusion steps", "value": value, "unit": "poses/s", "n_gpus": world,
@@ -362,18 +512,36 @@ def run_cuda(cli):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(cli, cli.poses), "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "poses/s", "h2d_bytes_per_step": h2d // N_SCHED,
-                        "d2h_bytes_per_step": int(final.numel() * 4 // N_SCHED), "seconds_per_run": float(t_e.item())},
-                "gpu_launches": prof['all_launches'], "roofline": roof, "roofline_tpconv_stream": stream_roof}
+                        "d2h_bytes_per_step": int(final.numel() * 4 // N_SCHED), "seconds_per_run": e2e_max,
+                        "runs_s": e2e_all, "how": "median of 3 sampling() calls after one warm call; each call collates the "
+                                                  "host poses, uploads one receptor copy + all ligands, captures the step graph, "
+                                                  "replays it 20 times and copies the final coordinates back"},
+                "gpu_launches": int(round(launches_per_step * cli.steps)), "launches_per_step": launches_per_step,
+                "graphed": w.graphed is not None, "eager_ms_per_step": eager_ms,
+                "roofline": roof, "roofline_tpconv_stream": stream_roof}
+        line.update(extra)
         if world == 1 and not cli.no_cpu_baseline:
             cores = host_threads()
             torch.set_num_threads(cores)
-            ostep = oracle_step_fn(args, cli.n_res, cli.n_atoms, seed=100)
+            ostep = oracle_step_fn(w.args, cli.n_res, cli.n_atoms, seed=100, want_scores=True)
+            t_idx = 10          # t = 0.5: mid-schedule edge count
             t0 = time.perf_counter()
-            ostep(10)           # t = 0.5: mid-schedule edge count
+            o_tr, o_rot, o_tor = ostep(t_idx, pos=ostep.pos0)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": 1.0 / (N_SCHED * dt), "unit": "poses/s", "cores": cores, "kind": "port",
-                                    "sample": f"1 pose-step (forward + pose update) of the same complex at t=0.5, "
-                                              f"{dt:.1f} s on {cores} host threads, oracle = reference op sequence restated"}
+                                    "sample": f"1 pose-step (forward + noise + pose update) of the same complex at t=0.5, "
+                                              f"{dt:.1f} s on {cores} host threads, oracle = reference op sequence restated; "
+                                              f"the reference arm (--impl reference) integrates the whole schedule"}
+            # parity of the timed workload: the product's scores for the same pose / same weights / same t
+            from diffdock_b200.diffusion_utils import set_time
+            g1 = collate(make_pose_list(1, n_res=cli.n_res, n_atoms=cli.n_atoms, seed=100, tr_sigma_max=w.args.tr_sigma_max)).to(dev)
+            t = w.sched[t_idx]
+            set_time(g1, None, t, t, t, 1, False, dev)
+            p_tr, p_rot, p_tor = w.model(g1)[:3]
+            rel = lambda a, b: float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+            line["parity"] = {"vs": "CPU oracle (reference op sequence), same synthetic complex, 1 pose, t=0.5, same weights",
+                              "tr_rel_err": rel(p_tr, o_tr), "rot_rel_err": rel(p_rot, o_rot),
+                              "tor_rel_err": rel(p_tor, o_tor) if o_tor.numel() else None, "tolerance": 1e-4}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -386,12 +554,13 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
-    ap.add_argument('--poses', type=int, default=32)
+    ap.add_argument('--poses', type=int, default=40)
     ap.add_argument('--n-res', dest='n_res', type=int, default=1500)
     ap.add_argument('--n-atoms', dest='n_atoms', type=int, default=40)
     ap.add_argument('--sh-lmax', dest='sh_lmax', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
+    ap.add_argument('--quick', action='store_true', help='skip the config-2 / CFG-L1 side measurements')
     ap.add_argument('--short-warmup', dest='short_warmup', action='store_true',
                     help='warm up exactly --warmup steps instead of a full schedule pass (runs under ncu)')
     cli = ap.parse_args()

@@ -199,13 +199,29 @@ class CGModel(nn.Module):
         B = data.num_graphs
         c = {}
         ei = rr.edge_index.long()
-        vec = (rec.pos[ei[1]] - rec.pos[ei[0]]).float()
-        rec_edge_attr = self.rec_edge_embedding(self.rec_distance_expansion(vec.norm(dim=-1)))
-        rec_node_attr = self.rec_node_embedding(rec.x)
-        ew = self.get_edge_weight(vec, self.rec_max_radius)
-        for layer in self.rec_emb_layers:
-            ea_ = torch.cat([rec_edge_attr, rec_node_attr[ei[0], :self.ns], rec_node_attr[ei[1], :self.ns]], -1)
-            rec_node_attr = layer(rec_node_attr, ei, ea_, None, edge_weight=ew, edge_vec=vec)
+        uniq = getattr(rec, '_unique', None)       # (nodes, edges, copies): the batch holds `copies` identical receptors
+        if uniq is not None and uniq[2] == B and uniq[0] * B == rec.pos.shape[0] and uniq[1] * B == ei.shape[1]:
+            # N poses of one complex (inference.py:236-239): embed the receptor ONCE and tile the result; the reference
+            # recomputes the identical 1280-wide embedding for every pose of the batch (models/cg_model.py:272-295)
+            n1, e1 = uniq[0], uniq[1]
+            ei1 = ei[:, :e1]
+            vec1 = (rec.pos[ei1[1]] - rec.pos[ei1[0]]).float()
+            ea1 = self.rec_edge_embedding(self.rec_distance_expansion(vec1.norm(dim=-1)))
+            na1 = self.rec_node_embedding(rec.x[:n1])
+            ew1 = self.get_edge_weight(vec1, self.rec_max_radius)
+            for layer in self.rec_emb_layers:
+                ea_ = torch.cat([ea1, na1[ei1[0], :self.ns], na1[ei1[1], :self.ns]], -1)
+                na1 = layer(na1, ei1, ea_, None, edge_weight=ew1, edge_vec=vec1)
+            vec, rec_edge_attr, rec_node_attr = vec1.repeat(B, 1), ea1.repeat(B, 1), na1.repeat(B, 1)
+            ew = ew1.repeat(B, 1) if torch.is_tensor(ew1) else ew1
+        else:
+            vec = (rec.pos[ei[1]] - rec.pos[ei[0]]).float()
+            rec_edge_attr = self.rec_edge_embedding(self.rec_distance_expansion(vec.norm(dim=-1)))
+            rec_node_attr = self.rec_node_embedding(rec.x)
+            ew = self.get_edge_weight(vec, self.rec_max_radius)
+            for layer in self.rec_emb_layers:
+                ea_ = torch.cat([rec_edge_attr, rec_node_attr[ei[0], :self.ns], rec_node_attr[ei[1], :self.ns]], -1)
+                rec_node_attr = layer(rec_node_attr, ei, ea_, None, edge_weight=ew, edge_vec=vec)
         rec.rec_node_attr, rr.rec_edge_attr, rr.edge_weight = rec_node_attr, rec_edge_attr, ew
         rr.edge_sh = None   # evaluated inside the convolution kernel from the edge vectors; kept for attribute parity
         # CSR order of the static receptor graph (target = edge_index[0])

@@ -393,6 +393,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
   const long long n_mtiles = (n_edges + BM - 1) / BM;
   const long long n_units = (n_mtiles + CG - 1) / CG;       // a unit = the CG edge tiles one MMA covers
   uint32_t pc = 0, mc = 0, ma = 0, ea = 0, mtc = 0, rc = 0;
+  long long dbg_c0 = 0;
+  unsigned long long dbg_g0 = 0;
+  if (DBG && blockIdx.x == 0 && tid == 0) {      // effective SM clock of this launch: clock64 ticks per globaltimer ns
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+  }
 
   for (long long unit = blockIdx.x / CG; unit < n_units; unit += gridDim.x / CG) {
     const long long mt = unit * CG + rank;                   // may be one past the end for the peer: all rows invalid
@@ -774,6 +780,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
     }
     if (tid == 0) { DBG_ADD(11, DBG_T() - t_unit); DBG_ADD(12, 1); }
     ++mtc;
+  }
+  if (DBG && blockIdx.x == 0 && tid == 0) {
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    DBG_ADD(25, clock64() - dbg_c0);
+    DBG_ADD(26, g1 - dbg_g0);
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();

@@ -11,13 +11,14 @@ from __future__ import annotations
 
 import copy
 import math
+import os
 
 import numpy as np
 import torch
 
 from . import ops
 from .diffusion_utils import set_time
-from .hetero import collate
+from .hetero import collate, collate_shared_receptor
 
 
 def is_iterable(arr):
@@ -83,6 +84,8 @@ def crop_receptor(g, cutoff):
     shared with ``g`` (the sampler keeps updating ``g['ligand'].pos``); like the reference's fresh Batch, the returned
     graph carries no cached receptor embeddings."""
     from .hetero import HeteroGraph, Store
+    if not isinstance(g, HeteroGraph):
+        raise NotImplementedError("device-side crop_beyond is written against diffdock_b200.hetero.HeteroGraph batches")
     lig, rec, rr = g['ligand'], g['receptor'], g['receptor', 'receptor']
     B = g.num_graphs
     lig_ptr = ops.segment_ptr(lig.batch, B)
@@ -114,14 +117,155 @@ def crop_receptor(g, cutoff):
     return out
 
 
+class GraphedSteps:
+    """All reverse-diffusion steps of one batch as replays of ONE CUDA graph.
+
+    The sync-free score model (diffdock_b200.CGModel._forward_sync_free) has static shapes for a given batch, the SDE
+    coefficients and schedule times of every step sit in device tables indexed by a device-side step counter, and the pose
+    update runs in place - so a step needs no host value at all: the 20 steps of utils/sampling.py:96-191 become 20 graph
+    launches (about 500 kernel launches each) with the host idle."""
+
+    def __init__(self, model, g, b, coef_rows, t_rows, bond_u, bond_v, mask_u8, use_torsion, device, draw_noise,
+                 philox=None, warmup=1):
+        self.g, self.b, self.device = g, b, device
+        lig = g['ligand']
+        self.pos = lig.pos = lig.pos.float().contiguous().clone()         # static buffer, updated in place
+        self.coef = torch.tensor(coef_rows, dtype=torch.float32, device=device).contiguous()        # [steps, 6]
+        self.times = torch.tensor(t_rows, dtype=torch.float32, device=device).contiguous()          # [steps, 3]
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+        n_lig, n_rec = lig.num_nodes, g['receptor'].num_nodes
+        names = ('tr', 'rot', 'tor')
+
+        def one_step():
+            t = self.times.index_select(0, self.step.long())[0]                                     # [3] on the device
+            for nt, n in (('ligand', n_lig), ('receptor', n_rec)):
+                g[nt].node_t = {k: t[i].expand(n) for i, k in enumerate(names)}
+            g.complex_t = {k: t[i].expand(b) for i, k in enumerate(names)}
+            tr, rot, tor = model(g)[:3]
+            tr, rot, tor = _nan_guard(tr, rot, tor)
+            has_tor = use_torsion and tor is not None and tor.numel() > 0
+            tr_z = rot_z = tor_z = None
+            if draw_noise and philox is None:
+                tr_z = torch.normal(mean=0, std=1, size=(b, 3), device=device)
+                rot_z = torch.normal(mean=0, std=1, size=(b, 3), device=device)
+                if has_tor:
+                    tor_z = torch.normal(mean=0, std=1, size=tuple(tor.shape), device=device)
+            ops.pose_update_dev(self.pos, b, bond_u, bond_v, mask_u8, tr, rot, tor if has_tor else None, self.coef,
+                                step_dev=self.step, tr_z=tr_z, rot_z=rot_z, tor_z=tor_z,
+                                seed=philox[0] if philox else 0, pose_key=philox[1] if philox else None,
+                                use_torsion=has_tor, out=self.pos)
+            self.step.add_(1)
+
+        pos0 = self.pos.clone()
+        # Outside the capture: the per-batch constants (receptor embedding, static CSR; they read sizes back to the host)
+        # and, the first time a model is used, one eager step (lazy library handles, kernel attributes, table uploads).
+        if hasattr(model, '_static'):
+            model._static(g)
+        n_warm = warmup if not getattr(model, '_graph_warmed', False) else 0
+        if n_warm:
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for _ in range(n_warm):
+                    one_step()
+            torch.cuda.current_stream(device).wait_stream(side)
+            try:
+                model._graph_warmed = True
+            except Exception:
+                pass
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            one_step()
+        self.pos.copy_(pos0)
+        self.step.zero_()
+
+    def run(self, n_steps):
+        for _ in range(n_steps):
+            self.graph.replay()
+        return self.pos
+
+
+def _collate_any(items, device):
+    """diffdock_b200 graphs: shared-receptor collate; torch_geometric HeteroData (what inference.py passes, utils/sampling.py:80):
+    PyG's own ``Batch.from_data_list`` - the score model only needs the attribute contract of SURVEY.md section 8(b)."""
+    from .hetero import HeteroGraph
+    if isinstance(items[0], HeteroGraph):
+        return collate_shared_receptor(items, device)
+    try:
+        from torch_geometric.data import Batch
+    except ImportError as e:
+        raise TypeError(f"cannot batch {type(items[0]).__name__} objects: pass diffdock_b200.hetero.HeteroGraph items, or "
+                        f"install torch_geometric for HeteroData lists") from e
+    return Batch.from_data_list(items).to(device)
+
+
+def _use_cuda_graph(model, model_args, noise_fn, visualization_list, N, batch_size, cuda_graph):
+    if cuda_graph is False or os.environ.get('DDB200_CUDA_GRAPH', '1') == '0':
+        return False
+    ok = (hasattr(model, 'sync_free_capable') and model.sync_free_capable() and noise_fn is None
+          and visualization_list is None and getattr(model_args, 'crop_beyond', None) is None)
+    if cuda_graph is True and not ok:
+        raise RuntimeError("cuda_graph=True needs the sync-free model path, no noise_fn / visualization / crop_beyond")
+    return ok
+
+
+def _eager_steps(g, b, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_schedule, t_to_sigma, model_args,
+                 coef_rows, device, bond_u, bond_v, mask_u8, use_torsion, ode, no_random, no_final_step_noise, noise_fn,
+                 n_noise, philox, visualization_list, data_list, batch_id, batch_size, n):
+    """The step loop launched op by op (utils/sampling.py:96-191): injected noise, per-step receptor cropping, visualisation,
+    or a score model whose shapes are outside the sync-free path."""
+    coef_dev = torch.tensor(coef_rows, dtype=torch.float32, device=device) if philox else None
+    for t_idx in range(inference_steps):
+        t_tr, t_rot, t_tor = tr_schedule[t_idx], rot_schedule[t_idx], tor_schedule[t_idx]
+        if getattr(model_args, 'crop_beyond', None) is not None:
+            tr_sigma = float(t_to_sigma(t_tr, t_rot, t_tor)[0])
+            mod = crop_receptor(g, tr_sigma * 3 + model_args.crop_beyond)
+        else:
+            mod = g
+        set_time(mod, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b,
+                 bool(getattr(model_args, 'all_atoms', False)), device)
+        tr_score, rot_score, tor_score = model(mod)[:3]
+        tr_score, rot_score, tor_score = _nan_guard(tr_score, rot_score, tor_score)
+        has_tor = use_torsion and tor_score.numel() > 0
+        if philox:        # in-kernel counter-based noise: the same draws as the graphed path
+            step_dev = torch.full((1,), t_idx, dtype=torch.int32, device=device)
+            g['ligand'].pos = ops.pose_update_dev(
+                g['ligand'].pos.float().contiguous(), b, bond_u, bond_v, mask_u8, tr_score, rot_score,
+                tor_score if has_tor else None, coef_dev, step_dev=step_dev, seed=philox[0], pose_key=philox[1],
+                use_torsion=has_tor)
+        else:
+            zero = no_random or (no_final_step_noise and t_idx == inference_steps - 1)
+            tr_z = rot_z = tor_z = None
+            if not ode and not zero:
+                draw = (lambda kind, shape: noise_fn(kind, shape).to(device)) if noise_fn is not None else \
+                    (lambda kind, shape: torch.normal(mean=0, std=1, size=shape, device=device))
+                tr_z = draw('tr', (n_noise, 3))
+                rot_z = draw('rot', (n_noise, 3))
+                if use_torsion:
+                    tor_z = draw('tor', tuple(tor_score.shape))
+            coef = list(coef_rows[t_idx])
+            g['ligand'].pos = ops.pose_update(g['ligand'].pos, b, bond_u, bond_v, mask_u8, tr_score, rot_score,
+                                              tor_score if has_tor else None, coef, tr_z, rot_z, tor_z, use_torsion=has_tor)
+        if visualization_list is not None:
+            for idx_b in range(b):
+                visualization_list[batch_id * batch_size + idx_b].add(
+                    (g['ligand'].pos[idx_b * n:n * (idx_b + 1)].detach().cpu()
+                     + data_list[batch_id * batch_size + idx_b].original_center.detach().cpu()), part=1, order=t_idx + 2)
+
+
 @torch.no_grad()
 def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
              no_random=False, ode=False, visualization_list=None, confidence_model=None, confidence_data_list=None,
              confidence_model_args=None, t_schedule=None, batch_size=32, no_final_step_noise=False, pivot=None,
              return_full_trajectory=False, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5, return_features=False,
-             noise_fn=None):
-    """``noise_fn(kind, shape) -> tensor`` (kind in 'tr','rot','tor') replaces the device RNG when given - used by the
-    injected-noise parity tests; otherwise torch.normal is drawn on ``device`` in the reference's order."""
+             noise_fn=None, cuda_graph=None, rng=None, seed=0, pose_keys=None):
+    """Same arguments and return value as ``utils/sampling.py:sampling``.  Extensions (all optional):
+    ``noise_fn(kind, shape) -> tensor`` (kind in 'tr','rot','tor') replaces the device RNG - used by the injected-noise parity
+    tests; otherwise torch.normal is drawn on ``device`` in the reference's order.
+    ``cuda_graph``: None = capture the step in a CUDA graph whenever possible, True = require it, False = eager steps.
+    ``rng='philox'``: noise from counter-based Philox streams keyed by (``seed``, ``pose_keys[i]``) and indexed by the step,
+    so the result for a pose does not depend on batch composition or on how poses are sharded over GPUs (SURVEY.md 8(e));
+    ``pose_keys`` [len(data_list)] int64 = (complex id << 32) | pose id, default 0..N-1."""
     assert not (return_full_trajectory or return_features or pivot), "Not implemented yet in new inference version"
     device = torch.device(device)
     if device.type != 'cuda':
@@ -140,40 +284,35 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     if confidence_model is not None and confidence_data_list is not None:
         conf_batches = [confidence_data_list[i:i + batch_size] for i in range(0, len(confidence_data_list), batch_size)]
 
+    philox = rng == 'philox'
+    assert rng in (None, 'philox'), "rng: None (torch.normal in the reference's order) or 'philox'"
+    if philox:
+        assert noise_fn is None
+        keys_all = torch.arange(N, dtype=torch.int64) if pose_keys is None else torch.as_tensor(pose_keys, dtype=torch.int64)
+    graphed = _use_cuda_graph(model, model_args, noise_fn, visualization_list, N, batch_size, cuda_graph)
+
     for batch_id, b0 in enumerate(range(0, N, batch_size)):
-        g = collate(data_list[b0:b0 + batch_size]).to(device, non_blocking=True)
+        g = _collate_any(data_list[b0:b0 + batch_size], device)
         b = g.num_graphs
         n = len(g['ligand'].pos) // b
+        keys = keys_all[b0:b0 + b].to(device) if philox else None
+        coef_rows, t_rows = [], []
         for t_idx in range(inference_steps):
-            t_tr, t_rot, t_tor = tr_schedule[t_idx], rot_schedule[t_idx], tor_schedule[t_idx]
             coef = step_coefficients(t_idx, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_to_sigma,
                                      model_args, ode, temp_sampling, temp_psi, temp_sigma_data)
-            if getattr(model_args, 'crop_beyond', None) is not None:
-                tr_sigma = float(t_to_sigma(t_tr, t_rot, t_tor)[0])
-                mod = crop_receptor(g, tr_sigma * 3 + model_args.crop_beyond)
-            else:
-                mod = g
-            set_time(mod, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b,
-                     bool(getattr(model_args, 'all_atoms', False)), device)
-            tr_score, rot_score, tor_score = model(mod)[:3]
-            tr_score, rot_score, tor_score = _nan_guard(tr_score, rot_score, tor_score)
-            zero = no_random or (no_final_step_noise and t_idx == inference_steps - 1)
-            tr_z = rot_z = tor_z = None
-            if not ode and not zero:
-                draw = (lambda kind, shape: noise_fn(kind, shape).to(device)) if noise_fn is not None else \
-                    (lambda kind, shape: torch.normal(mean=0, std=1, size=shape, device=device))
-                tr_z = draw('tr', (min(batch_size, N), 3))
-                rot_z = draw('rot', (min(batch_size, N), 3))
-                if use_torsion:
-                    tor_z = draw('tor', tuple(tor_score.shape))
-            g['ligand'].pos = ops.pose_update(g['ligand'].pos, b, bond_u, bond_v, mask_u8, tr_score, rot_score,
-                                              tor_score if use_torsion and tor_score.numel() else None, coef,
-                                              tr_z, rot_z, tor_z, use_torsion=use_torsion and tor_score.numel() > 0)
-            if visualization_list is not None:
-                for idx_b in range(b):
-                    visualization_list[batch_id * batch_size + idx_b].add(
-                        (g['ligand'].pos[idx_b * n:n * (idx_b + 1)].detach().cpu()
-                         + data_list[batch_id * batch_size + idx_b].original_center.detach().cpu()), part=1, order=t_idx + 2)
+            if ode or no_random or (no_final_step_noise and t_idx == inference_steps - 1):
+                coef[1] = coef[3] = coef[5] = 0.0          # no noise in this step (utils/sampling.py:136-145,158-161)
+            coef_rows.append(coef)
+            t_rows.append([float(tr_schedule[t_idx]), float(rot_schedule[t_idx]), float(tor_schedule[t_idx])])
+        if graphed and t_schedule is None and b > 0:
+            steps = GraphedSteps(model, g, b, coef_rows, t_rows, bond_u, bond_v, mask_u8, use_torsion, device,
+                                 draw_noise=not (ode or no_random), philox=(seed, keys) if philox else None)
+            steps.run(inference_steps)
+        else:
+            _eager_steps(g, b, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_schedule, t_to_sigma,
+                         model_args, coef_rows, device, bond_u, bond_v, mask_u8, use_torsion, ode, no_random,
+                         no_final_step_noise, noise_fn, min(batch_size, N), (seed, keys) if philox else None,
+                         visualization_list, data_list, batch_id, batch_size, n)
         for i in range(b):
             data_list[b0 + i]['ligand'].pos = g['ligand'].pos[i * n:n * (i + 1)]
         if confidence_model is not None:

@@ -69,4 +69,5 @@ if __name__ == '__main__':
         r['clk_per_cta_unit'] = {NAMES[i]: int(dbg[i]) * (2 if (pair and i in one_cta) else 1) // units for i in NAMES if i != 12}
         r['units'] = units // 5
         r['issue_clk_per_mma'] = round(dbg[13] / max(dbg[14], 1), 1)
+        r['sm_clock_ghz_in_kernel'] = round(dbg[25] / max(dbg[26], 1), 3)     # clock64 ticks per globaltimer ns, CTA 0
     print(json.dumps(r), flush=True)
