@@ -45,8 +45,8 @@ def get_t_schedule(sigma_schedule='expbeta', inference_steps=20, inf_sched_alpha
 
 def set_time(complex_graphs, t, t_tr, t_rot, t_tor, batchsize, all_atoms, device, include_miscellaneous_atoms=False):
     """Writes node_t / complex_t like utils/diffusion_utils.py:146-168 - one fill per tensor, created on the device."""
-    assert not all_atoms and not include_miscellaneous_atoms, "coarse-grained score model only"
-    for nt in ('ligand', 'receptor'):
+    assert not include_miscellaneous_atoms, "miscellaneous atoms are outside the hot-path scope"
+    for nt in ('ligand', 'receptor') + (('atom',) if all_atoms else ()):
         n = complex_graphs[nt].num_nodes
         complex_graphs[nt].node_t = {'tr': torch.full((n,), float(t_tr), device=device),
                                      'rot': torch.full((n,), float(t_rot), device=device),

@@ -16,6 +16,7 @@ from .hetero import HeteroGraph
 # vocabulary sizes: datasets/process_mols.py:59-76 (ligand atoms), :85-87 (residues)
 LIG_FEATURE_DIMS = ([119, 4, 12, 12, 8, 10, 6, 6, 2, 8, 2, 2, 2, 2, 2, 2], 0)
 REC_RESIDUE_FEATURE_DIMS = ([38], 0)
+REC_ATOM_FEATURE_DIMS = ([38, 119, 23, 38], 0)   # datasets/process_mols.py:78-83 (residue type, atomic number, two atom-name classes)
 LM_EMBED_DIM = 1280  # ESM2-650M, models/cg_model.py:73-74
 
 
@@ -125,9 +126,39 @@ def _random_rotation(rng):
                      [2 * (i * k - j * r), 2 * (j * k + i * r), 1 - 2 * (i * i + j * j)]])
 
 
+def _receptor_atoms(rpos, res_type, rng, atom_cutoff, atom_max_neighbors):
+    """All-atom receptor nodes in the layout of datasets/process_mols.py:203-239: 3-7 atoms scattered ~1.5 A around every
+    residue position; ('atom','atom') contact edges stored as [neighbour, centre] (all atoms within ``atom_cutoff``, the
+    nearest ``atom_max_neighbors`` if there are more, the nearest one if there is none); ('atom','receptor') edges
+    [atom, its residue]; features = (residue type, atomic number, atom-name class 2, atom-name class 3)."""
+    n_res = rpos.shape[0]
+    counts = rng.integers(3, 8, size=n_res)
+    res_of = np.repeat(np.arange(n_res), counts)
+    apos = (rpos[res_of] + rng.normal(scale=1.5, size=(len(res_of), 3))).astype(np.float32)
+    dims = REC_ATOM_FEATURE_DIMS[0]
+    ax = np.stack([res_type[res_of].astype(np.int64)] + [rng.integers(0, d, size=len(res_of)) for d in dims[1:]], 1).astype(np.float32)
+    src, dst = [], []
+    for s in range(0, len(apos), 512):
+        d = np.linalg.norm(apos[s:s + 512, None, :] - apos[None, :, :], axis=-1)
+        for i in range(d.shape[0]):
+            row = d[i].copy()
+            row[s + i] = np.inf
+            nb = np.where(row < atom_cutoff)[0]
+            if len(nb) > atom_max_neighbors:
+                nb = np.argsort(row, kind='stable')[:atom_max_neighbors]
+            if len(nb) == 0:
+                nb = np.argsort(row, kind='stable')[:1]
+            src.extend(nb.tolist())
+            dst.extend([s + i] * len(nb))
+    aa_edge = np.stack([np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)], 0)
+    ar_edge = np.stack([np.arange(len(res_of), dtype=np.int64), res_of.astype(np.int64)], 0)
+    return apos, ax, aa_edge, ar_edge
+
+
 def make_complex(n_res=200, n_atoms=20, seed=0, max_neighbors=24, rec_radius=15.0, name=None,
-                 lm_dim=LM_EMBED_DIM) -> HeteroGraph:
-    """One synthetic complex (CPU tensors).  Ligand is placed half-way between receptor centre and surface."""
+                 lm_dim=LM_EMBED_DIM, all_atoms=False, atom_cutoff=5.0, atom_max_neighbors=8) -> HeteroGraph:
+    """One synthetic complex (CPU tensors).  Ligand is placed half-way between receptor centre and surface.
+    ``all_atoms``: also the receptor-atom nodes and edges the all-atom models read (models/old_aa_model.py:424-486)."""
     rng = np.random.default_rng(seed)
     rpos, redge, rx, R = _receptor(n_res, rng, max_neighbors, rec_radius)
     if lm_dim != LM_EMBED_DIM:
@@ -152,6 +183,13 @@ def make_complex(n_res=200, n_atoms=20, seed=0, max_neighbors=24, rec_radius=15.
     # carried (and cropped) by utils/utils.py:crop_beyond; not read by the coarse-grained score model
     rec.side_chain_vecs = torch.from_numpy(np.random.default_rng(seed + 7919).normal(size=(n_res, 4, 3)).astype(np.float32))
     g['receptor', 'receptor'].edge_index = torch.from_numpy(redge)
+    if all_atoms:
+        apos, ax, aa_edge, ar_edge = _receptor_atoms(rpos, rx[:, 0], np.random.default_rng(seed + 104729), atom_cutoff,
+                                                     atom_max_neighbors)
+        g['atom'].x = torch.from_numpy(ax)
+        g['atom'].pos = torch.from_numpy(apos)
+        g['atom', 'atom'].edge_index = torch.from_numpy(aa_edge)
+        g['atom', 'receptor'].edge_index = torch.from_numpy(ar_edge)
     return g
 
 
@@ -177,6 +215,20 @@ def randomize_pose(g: HeteroGraph, seed, tr_sigma_max, no_torsion=False) -> Hete
     return g
 
 
-def make_pose_list(n_poses, n_res=200, n_atoms=20, seed=0, tr_sigma_max=19.0, **kw):
+def make_pose_list(n_poses, n_res=200, n_atoms=20, seed=0, tr_sigma_max=19.0, share_receptor=False, **kw):
+    """``n_poses`` prior samples of one synthetic complex.  Default: every pose is a deep copy of the complex, like
+    inference.py:236-239; ``share_receptor=True`` lets the poses share the receptor tensors (same storage), which keeps a
+    many-complex workload (BASELINE config 5) small on the host."""
     base = make_complex(n_res, n_atoms, seed, **kw)
-    return [randomize_pose(base, seed * 100003 + 17 * p + 1, tr_sigma_max) for p in range(n_poses)]
+    poses = [randomize_pose(base, seed * 100003 + 17 * p + 1, tr_sigma_max) for p in range(n_poses)]
+    if share_receptor:
+        for g in poses[1:]:
+            g._nodes['receptor'] = poses[0]._nodes['receptor']
+            g._edges[('receptor', 'receptor')] = poses[0]._edges[('receptor', 'receptor')]
+    return poses
+
+
+def config5_sizes(n_complexes=64, seed=0):
+    """BASELINE config 5 / SURVEY 8(d): N_r ~ U(200, 600), N_l ~ U(15, 50) per complex (seeded)."""
+    rng = np.random.default_rng(seed)
+    return [(int(rng.integers(200, 601)), int(rng.integers(15, 51))) for _ in range(n_complexes)]

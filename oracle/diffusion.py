@@ -19,9 +19,9 @@ def get_t_schedule(inference_steps, inf_sched_alpha=1, inf_sched_beta=1, t_max=1
     return beta.ppf(c, a=inf_sched_alpha, b=inf_sched_beta)
 
 
-def set_time(g, t_tr, t_rot, t_tor, batchsize, device):
-    """utils/diffusion_utils.py:146-168 (all_atoms=False)."""
-    for nt in ('ligand', 'receptor'):
+def set_time(g, t_tr, t_rot, t_tor, batchsize, device, all_atoms=False):
+    """utils/diffusion_utils.py:146-168."""
+    for nt in ('ligand', 'receptor') + (('atom',) if all_atoms else ()):
         n = g[nt].num_nodes
         g[nt].node_t = {'tr': t_tr * torch.ones(n).to(device), 'rot': t_rot * torch.ones(n).to(device),
                         'tor': t_tor * torch.ones(n).to(device)}

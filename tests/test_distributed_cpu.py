@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from diffdock_b200.distributed import shard_bounds
+from diffdock_b200.distributed import assign_balanced, shard_bounds
 
 
 def test_shard_bounds_cover_and_balance():
@@ -43,3 +43,43 @@ def test_two_rank_sharded_sampling_gathers_all_poses():
         ret = mgr.dict()
         mp.spawn(_worker, args=(2, port, n_poses, ret), nprocs=2, join=True)
         assert ret[0] and ret[1]
+
+
+def test_assign_balanced_is_deterministic_and_balanced():
+    import random
+    rnd = random.Random(0)
+    costs = [rnd.randint(200, 600) * rnd.randint(15, 50) for _ in range(64)]
+    for w in (1, 2, 4, 8):
+        parts = assign_balanced(costs, w)
+        assert sorted(i for p in parts for i in p) == list(range(64)) and parts == assign_balanced(costs, w)
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) <= 1.05 * sum(costs) / w + max(costs) * 0.25
+    assert assign_balanced([1.0, 1.0], 4) == [[0], [1], [], []]
+
+
+def _worker_complexes(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from diffdock_b200.distributed import sample_complexes_sharded
+    sizes = [(3, 5), (4, 7), (2, 9), (5, 4), (3, 6)]            # (poses, atoms) per complex
+    shapes = [(p, a, 3) for p, a in sizes]
+    calls = []
+
+    def sample_one(i):                                           # value depends on the complex only
+        calls.append(i)
+        p, a = sizes[i]
+        return torch.arange(p * a * 3, dtype=torch.float32).reshape(p, a, 3) + 1000 * i
+
+    out = sample_complexes_sharded(len(sizes), [p * a for p, a in sizes], shapes, sample_one)
+    ok = all(torch.equal(out[i], torch.arange(p * a * 3, dtype=torch.float32).reshape(p, a, 3) + 1000 * i)
+             for i, (p, a) in enumerate(sizes))
+    ret[rank] = (ok, sorted(calls))
+    dist.destroy_process_group()
+
+
+def test_two_rank_complex_sharding_gathers_every_complex():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_complexes, args=(2, 29621, ret), nprocs=2, join=True)
+    assert ret[0][0] and ret[1][0]
+    assert sorted(ret[0][1] + ret[1][1]) == [0, 1, 2, 3, 4] and ret[0][1] and ret[1][1]      # disjoint, both ranks worked

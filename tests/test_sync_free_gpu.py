@@ -160,3 +160,31 @@ def test_philox_known_answer_and_moments(built_lib):
     torch.cuda.synchronize()
     assert abs(float(zz.mean())) < 0.01 and abs(float(zz.var()) - 1.0) < 0.02 and float(zz.abs().max()) < 6.5
     assert abs(float((zz[0::4] * zz[1::4]).mean())) < 0.01
+
+
+def test_complex_sharding_result_independent_of_world_size(built_lib):
+    """Level-1 partitioning (whole complexes per rank) emulated on one GPU: the jobs of a 1-rank and of a 3-rank
+    assignment are executed one after another and must give the same coordinates for every complex - each complex is always
+    one batch (so even the batch-dependent default centre convolution cannot tell the difference) and its noise is keyed by
+    (complex, pose, step)."""
+    from diffdock_b200.distributed import assign_balanced
+    from diffdock_b200.synthetic import make_pose_list
+    args = _args()
+    _, p = make_model_pair(args, seed=23)
+    sizes = [(40, 9), (70, 14), (55, 11), (30, 8)]
+    costs = [r * a for r, a in sizes]
+
+    def sample_one(i):
+        poses = make_pose_list(3, n_res=sizes[i][0], n_atoms=sizes[i][1], seed=70 + i, tr_sigma_max=args.tr_sigma_max,
+                               share_receptor=True)
+        return _sample(p, args, poses, rng='philox', seed=9, pose_keys=(i << 32) + torch.arange(3))
+
+    results = {}
+    for world in (1, 3):
+        out = {}
+        for rank_items in assign_balanced(costs, world):
+            for i in rank_items:                      # what rank r would run, in its order
+                out[i] = sample_one(i)
+        results[world] = out
+    for i in range(len(sizes)):
+        assert float((results[1][i] - results[3][i]).abs().max()) < 2e-3
