@@ -29,6 +29,7 @@ SIGNATURES = {
     'ddb200_philox_probe': (_int, [C.c_uint64, _i64, C.c_uint32, C.c_uint32, _int, _vp, _vp, _vp]),
     'ddb200_graph_fill': (_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _int, _vp, _int, _int, _vp]),
+    'ddb200_csr_sort_by_target': (_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ddb200_edge_embed': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, C.c_float, _i64, _vp, _vp, _vp]),
     'ddb200_radial_gemm': (_int, [_vp, _i64, _i64, _int, _vp, _vp, _int, _vp, _i64, _vp]),
     'ddb200_radial_mlp': (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _i64, _vp,

@@ -9,9 +9,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/diffdock_b200.h"
 
 namespace {
+
+__global__ void iota_kernel(int* p, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int)i;
+}
+// row_ptr[v] = first position of a key >= v in the sorted key array (v = 0 .. n_rows)
+__global__ void row_ptr_kernel(const int* __restrict__ keys, long long n, int n_rows, int* __restrict__ row_ptr) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > n_rows) return;
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (keys[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  row_ptr[v] = (int)lo;
+}
 
 template <bool FILL>
 __global__ void radius_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ x_ptr,
@@ -268,6 +286,37 @@ int ddb200_edge_embed(const float* edge_vec, const int32_t* edge_row, const floa
   DDB200_EMBED_CASE(16, 16) DDB200_EMBED_CASE(8, 16) DDB200_EMBED_CASE(16, 24) DDB200_EMBED_CASE(8, 24)
 #undef DDB200_EMBED_CASE
   return DDB200_EINVAL;
+}
+
+
+// Stable sort of an edge list by its convolution target (CSR order) without any host round trip: LSD radix sort of the
+// int32 keys with the edge ids as values (cub::DeviceRadixSort::SortPairs, stable), then the CSR row pointer by binary search.
+int ddb200_csr_sort_by_target(const int32_t* tgt, int64_t n_edges, int32_t n_rows, int32_t* tgt_sorted, int32_t* perm,
+                              int32_t* row_ptr, void* workspace, size_t* workspace_bytes, void* stream) {
+  if (!workspace_bytes || n_edges < 0 || n_rows < 0 || n_edges > 0x7fffffffLL) return DDB200_EINVAL;
+  size_t cub_bytes = 0;
+  int end_bit = 1;
+  while (end_bit < 31 && (1LL << end_bit) <= (long long)n_rows) ++end_bit;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
+                                                  (int*)nullptr, (int)n_edges, 0, end_bit, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  const size_t ids_bytes = ((size_t)n_edges * sizeof(int) + 255) / 256 * 256;
+  const size_t need = ids_bytes + cub_bytes;
+  if (!workspace) {                       // size query
+    *workspace_bytes = need;
+    return 0;
+  }
+  if (*workspace_bytes < need || !tgt || !tgt_sorted || !perm) return DDB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_edges > 0) {
+    int* ids = reinterpret_cast<int*>(workspace);
+    iota_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(ids, n_edges);
+    e = cub::DeviceRadixSort::SortPairs(reinterpret_cast<char*>(workspace) + ids_bytes, cub_bytes, tgt, tgt_sorted, ids, perm,
+                                        (int)n_edges, 0, end_bit, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (row_ptr) row_ptr_kernel<<<(unsigned)((n_rows + 1 + 255) / 256), 256, 0, st>>>(tgt_sorted, n_edges, n_rows, row_ptr);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

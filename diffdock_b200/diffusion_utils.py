@@ -26,11 +26,26 @@ def sinusoidal_embedding(timesteps, embedding_dim, max_positions=10000):
     return emb
 
 
+class GaussianFourierProjection(torch.nn.Module):
+    """Gaussian Fourier embedding of the noise level (utils/diffusion_utils.py:113-125): a fixed random projection W drawn at
+    construction (non-trainable parameter, so that it follows ``.to(device)`` and sits in the module's state_dict)."""
+
+    def __init__(self, embedding_size=256, scale=1.0):
+        super().__init__()
+        self.W = torch.nn.Parameter(torch.randn(embedding_size // 2) * scale, requires_grad=False)
+
+    def forward(self, x):
+        x_proj = x[:, None] * self.W[None, :] * 2 * np.pi
+        return torch.cat([torch.sin(x_proj), torch.cos(x_proj)], dim=-1)
+
+
 def get_timestep_embedding(embedding_type, embedding_dim, embedding_scale=10000):
-    if embedding_type != 'sinusoidal':
-        raise NotImplementedError("only the sinusoidal time embedding is built (the 'fourier' one carries a random "
-                                  "projection that lives in the checkpoint)")
-    return lambda x: sinusoidal_embedding(embedding_scale * x, embedding_dim)
+    """utils/diffusion_utils.py:128-135."""
+    if embedding_type == 'sinusoidal':
+        return lambda x: sinusoidal_embedding(embedding_scale * x, embedding_dim)
+    if embedding_type == 'fourier':
+        return GaussianFourierProjection(embedding_size=embedding_dim, scale=embedding_scale)
+    raise NotImplementedError(embedding_type)
 
 
 def get_t_schedule(sigma_schedule='expbeta', inference_steps=20, inf_sched_alpha=1, inf_sched_beta=1, t_max=1):

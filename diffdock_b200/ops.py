@@ -283,3 +283,25 @@ def pose_update_dev(pos, n_poses, bond_u, bond_v, mask_rotate_u8, tr_score, rot_
     _lib.check(rc, 'ddb200_pose_update_dev')
     PROFILE.all_launches += 1
     return out
+
+
+def csr_sort_by_target(tgt32, n_rows, want_row_ptr=False):
+    """Stable device-side sort of an edge list by target: (tgt_sorted int32, perm int64, row_ptr int32 | None);
+    ddb200_csr_sort_by_target with a torch-allocated workspace.  No host synchronisation."""
+    _need_cuda(tgt32)
+    assert tgt32.dtype == torch.int32 and tgt32.is_contiguous()
+    n = tgt32.shape[0]
+    dev = tgt32.device
+    L = _lib.lib()
+    need = C.c_size_t(0)
+    _lib.check(L.ddb200_csr_sort_by_target(None, n, int(n_rows), None, None, None, None, C.byref(need), _stream()),
+               'ddb200_csr_sort_by_target(size)')
+    ws = torch.empty(max(int(need.value), 1), dtype=torch.uint8, device=dev)
+    out_t = torch.empty_like(tgt32)
+    perm = torch.empty_like(tgt32)
+    rp = torch.empty(int(n_rows) + 1, dtype=torch.int32, device=dev) if want_row_ptr else None
+    have = C.c_size_t(ws.numel())
+    _lib.check(L.ddb200_csr_sort_by_target(_ptr(tgt32), n, int(n_rows), _ptr(out_t), _ptr(perm), _ptr(rp), _ptr(ws),
+                                           C.byref(have), _stream()), 'ddb200_csr_sort_by_target')
+    PROFILE.all_launches += 2 + (1 if want_row_ptr else 0)
+    return out_t, perm.long(), rp

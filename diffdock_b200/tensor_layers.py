@@ -271,12 +271,13 @@ class TensorProductConvLayer(nn.Module):
             if e > s:
                 tgt, src = edge_index[0, s:e], edge_index[1, s:e]
                 geo, ew = geo_all[s:e], (ew_all[s:e].reshape(-1) if ew_all is not None else None)
-                if not assume_sorted:
-                    tgt, order = torch.sort(tgt, stable=True)
+                tgt = tgt.to(torch.int32).contiguous()
+                if not assume_sorted:        # CSR order by target: stable device radix sort (ddb200_csr_sort_by_target)
+                    tgt, order, _ = ops.csr_sort_by_target(tgt, max(n_out, 1))
                     src, geo, ea = src[order], geo[order], ea[order]
                     if ew is not None:
                         ew = ew[order]
-                prepared.append((tgt.to(torch.int32).contiguous(), src.to(torch.int32).contiguous(), ea, geo.contiguous(), ew))
+                prepared.append((tgt, src.to(torch.int32).contiguous(), ea, geo.contiguous(), ew))
             else:
                 prepared.append(None)
             s = e
@@ -372,6 +373,18 @@ class OldTensorProductConvLayer(TensorProductConvLayer):
     @torch.no_grad()
     def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0,
                 edge_vec=None, assume_sorted=False, gather_scalars=0):
+        if edge_index.shape[1] == 0:
+            # No edge at all (e.g. a pose without any receptor atom within 5 A): the reference divides the edges into zero
+            # chunks and raises (np.array_split, models/tensor_layers.py:362-365).  Here the convolution contributes zeros
+            # to its out_nodes rows and the usual epilogue (residual, BatchNorm) follows.
+            n_out = int(out_nodes) if out_nodes else node_attr.shape[0]
+            out = node_attr.new_zeros((n_out, self.out_size), dtype=torch.float32)
+            if self.residual:
+                out = out + F.pad(node_attr.float(), (0, out.shape[-1] - node_attr.shape[-1]))
+            if self.batch_norm is not None:
+                scale, shift = self.batch_norm.fold()
+                out = out * scale + shift
+            return out.to(node_attr.dtype)
         if not self.residual:
             return super().forward(node_attr, edge_index, edge_attr, edge_sh, out_nodes, reduce, edge_weight,
                                    edge_vec=edge_vec, assume_sorted=assume_sorted, gather_scalars=gather_scalars)

@@ -15,6 +15,7 @@
 #ifndef DIFFDOCK_B200_H
 #define DIFFDOCK_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -147,6 +148,16 @@ int ddb200_graph_fill(const float* x, const float* y, const int32_t* x_ptr, cons
                       const int32_t* row_start, const int32_t* pre_ptr, const int32_t* pre_col, int32_t* out_row,
                       int32_t* out_col, float* out_vec, int32_t* out_eid, int32_t* slot_out, const int32_t* slot_in,
                       const int32_t* y_ptr, int slot_ld, int32_t* out_perm, int row_offset, int col_offset, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * CSR order of an arbitrary edge list: stable sort by target (keys tgt [n_edges] int32 in [0, n_rows)), device only.
+ *   tgt_sorted [n_edges], perm [n_edges] (perm[p] = original position of the edge now at p), row_ptr [n_rows + 1] or NULL.
+ * Two-call workspace protocol (nothing is allocated here): workspace == NULL writes the required size to *workspace_bytes;
+ * otherwise *workspace_bytes is the size of the caller's device buffer.
+ * Replaces: the per-layer implicit ordering work of torch_scatter (models/tensor_layers.py:220); SURVEY.md section 8(b).
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_csr_sort_by_target(const int32_t* tgt, int64_t n_edges, int32_t n_rows, int32_t* tgt_sorted, int32_t* perm,
+                              int32_t* row_ptr, void* workspace, size_t* workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Ligand-receptor edge embedding, one kernel, live edge count on the device:

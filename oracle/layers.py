@@ -2,6 +2,7 @@
 TEST INFRASTRUCTURE (see oracle/__init__.py)."""
 import math
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -105,7 +106,21 @@ def sinusoidal_embedding(timesteps, embedding_dim, max_positions=10000):
     return emb
 
 
+class GaussianFourierProjection(nn.Module):
+    """utils/diffusion_utils.py:113-125."""
+
+    def __init__(self, embedding_size=256, scale=1.0):
+        super().__init__()
+        self.W = nn.Parameter(torch.randn(embedding_size // 2) * scale, requires_grad=False)
+
+    def forward(self, x):
+        x_proj = x[:, None] * self.W[None, :] * 2 * np.pi
+        return torch.cat([torch.sin(x_proj), torch.cos(x_proj)], dim=-1)
+
+
 def get_timestep_embedding(embedding_type, embedding_dim, embedding_scale=10000):
-    """utils/diffusion_utils.py:128-135 ('sinusoidal' only; 'fourier' carries a random parameter W)."""
-    assert embedding_type == 'sinusoidal'
-    return lambda x: sinusoidal_embedding(embedding_scale * x, embedding_dim)
+    """utils/diffusion_utils.py:128-135."""
+    if embedding_type == 'sinusoidal':
+        return lambda x: sinusoidal_embedding(embedding_scale * x, embedding_dim)
+    assert embedding_type == 'fourier'
+    return GaussianFourierProjection(embedding_size=embedding_dim, scale=embedding_scale)

@@ -167,19 +167,26 @@ def golden_model(case, which):
     return m.to(dev), poses, a
 
 
-def golden_confidence_model(case, which):
-    """Confidence model ('oracle' on CPU | 'product' on cuda:0) + pose list rebuilt from a ref_confidence.pt case."""
+def golden_confidence_model(case, which, all_atoms=False):
+    """Confidence model ('oracle' on CPU | 'product' on cuda:0) + pose list rebuilt from a ref_confidence.pt case
+    (``all_atoms``: a ref_confidence_aa.pt case, models/old_aa_model.py)."""
     from functools import partial
     from diffdock_b200.hetero import graph_from_dict
     from diffdock_b200.synthetic import default_model_args
     a = default_model_args()
     if which == 'oracle':
-        from oracle.old_cg_model import CGOldModel
+        if all_atoms:
+            from oracle.old_aa_model import AAOldModel as CGOldModel
+        else:
+            from oracle.old_cg_model import CGOldModel
         from oracle.layers import get_timestep_embedding
         from oracle.diffusion import t_to_sigma
         dev = 'cpu'
     else:
-        from diffdock_b200.old_cg_model import CGOldModel
+        if all_atoms:
+            from diffdock_b200.old_aa_model import AAOldModel as CGOldModel
+        else:
+            from diffdock_b200.old_cg_model import CGOldModel
         from diffdock_b200.diffusion_utils import get_timestep_embedding, t_to_sigma
         dev = torch.device('cuda:0')
     kw = dict(case['kw'])

@@ -175,3 +175,36 @@ def test_to_data_list_inverts_collate():
         assert torch.equal(p['ligand'].pos, q['ligand'].pos) and torch.equal(p['ligand'].edge_mask, q['ligand'].edge_mask)
         assert torch.equal(p['receptor', 'receptor'].edge_index, q['receptor', 'receptor'].edge_index)
         assert torch.equal(p['ligand', 'ligand'].edge_index, q['ligand', 'ligand'].edge_index)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_oracle_all_atom_confidence_matches_reference_fixture(idx):
+    """oracle/old_aa_model.py vs the unmodified models/old_aa_model.py (tests/golden/make_golden_confidence_aa.py):
+    nine convolutions per layer over ligand atoms, residues and receptor atoms, affinity head in case 2."""
+    import copy
+    from diffdock_b200.hetero import collate
+    from oracle.diffusion import set_time
+    from tests.parity_helpers import golden_confidence_model, load_golden
+    case = load_golden('ref_confidence_aa.pt')[idx]
+    m, poses = golden_confidence_model(case, 'oracle', all_atoms=True)
+    b = collate(copy.deepcopy(poses))
+    set_time(b, 0, 0, 0, len(poses), 'cpu', all_atoms=True)
+    with torch.no_grad():
+        conf = m(b)
+    ref = case['confidence']
+    assert conf.shape == ref.shape
+    assert float((conf - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_fourier_time_embedding_matches_reference_fixture():
+    """utils/diffusion_utils.py:113-135 (GaussianFourierProjection): same RNG draw for W at the same seed, same output -
+    oracle and product."""
+    from tests.parity_helpers import load_golden
+    from oracle.layers import get_timestep_embedding as o_emb
+    from diffdock_b200.diffusion_utils import get_timestep_embedding as p_emb
+    ref = load_golden('ref_fourier.pt')
+    for make in (o_emb, p_emb):
+        torch.manual_seed(ref['seed'])
+        emb = make('fourier', ref['dim'], ref['scale'])
+        assert torch.equal(emb.W, ref['W']) and list(emb.state_dict().keys()) == ['W']
+        assert float((emb(ref['x']) - ref['out']).abs().max()) == 0.0
