@@ -267,7 +267,9 @@ class CGModel(nn.Module):
         c['pre_ptr'], c['pre_cnt'] = ptr, i32(cnt)
         attr = ll.edge_attr.float()[order] if ei.shape[1] else torch.zeros((0, self.in_lig_edge_features), device=dev)
         c['pre_attr'] = torch.cat([attr, torch.zeros((1, attr.shape[1]), device=dev)], 0)     # row -1: "not a bond"
-        c['cap_ll'] = int(ei.shape[1]) + 32 * n_lig
+        # radius_graph(max_num_neighbors=32) = radius with cap 33 minus the self hit: an atom whose own index is not among its
+        # first 33 hits keeps 33 neighbours
+        c['cap_ll'] = int(ei.shape[1]) + 33 * n_lig
         c['bond_lig_batch'] = lig.batch[c['bonds'][0]] if c['n_bonds'] else None
         c['cap_tor'] = 32 * c['n_bonds']
         c['bond_batch32'] = i32(c['bond_batch']) if c['n_bonds'] else None

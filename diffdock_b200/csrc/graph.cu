@@ -306,7 +306,7 @@ int ddb200_csr_sort_by_target(const int32_t* tgt, int64_t n_edges, int32_t n_row
     *workspace_bytes = need;
     return 0;
   }
-  if (*workspace_bytes < need || !tgt || !tgt_sorted || !perm) return DDB200_EINVAL;
+  if (*workspace_bytes < need || (n_edges > 0 && (!tgt || !tgt_sorted || !perm))) return DDB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (n_edges > 0) {
     int* ids = reinterpret_cast<int*>(workspace);

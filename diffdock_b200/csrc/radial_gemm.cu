@@ -81,6 +81,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// exactly one lane of the (converged) warp gets true: the single-thread instructions (bulk copies, tcgen05.mma / commit) are
+// issued under this predicate from warp-uniform loops - under `if (lane == 0)` the compiler wraps every one of them in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~95 clocks per tcgen05.mma, measured on the fused kernel)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -232,36 +240,42 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
 
     if (warp == 0) {
       // ===== B producer =====================================================================================
-      if (lane == 0) {
+      {   // warp-uniform loops, one elected lane issues
         if (fuse1)
           for (int kb = 0; kb < p.n_kb1; ++kb, ++pc) {
             const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&full[s], B_STAGE_BYTES);
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.w1img) + (size_t)kb * B_STAGE_BYTES;
-            if constexpr (CL == 1) {
-              bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s]);
-            } else if (crank == 0) {
-              bulk_g2s_mcast(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s], kMask);
+            if (elect_one()) {
+              mbar_expect_tx(&full[s], B_STAGE_BYTES);
+              if constexpr (CL == 1) {
+                bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s]);
+              } else if (crank == 0) {
+                bulk_g2s_mcast(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s], kMask);
+              }
             }
+            __syncwarp();
           }
         for (int nt = 0; nt < p.n_tiles_n; ++nt)
           for (int kb = 0; kb < p.n_kb; ++kb, ++pc) {
             const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
             mbar_wait(&empty[s], ph ^ 1);       // all CL CTAs have consumed this stage
-            mbar_expect_tx(&full[s], B_STAGE_BYTES);
             const unsigned char* src =
                 reinterpret_cast<const unsigned char*>(p.bimg) + ((size_t)nt * p.n_kb + kb) * B_STAGE_BYTES;
-            if constexpr (CL == 1) {
-              bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s]);
-            } else if (crank == 0) {
-              bulk_g2s_mcast(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s], kMask);
+            if (elect_one()) {
+              mbar_expect_tx(&full[s], B_STAGE_BYTES);
+              if constexpr (CL == 1) {
+                bulk_g2s(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s]);
+              } else if (crank == 0) {
+                bulk_g2s_mcast(sB + (size_t)s * B_STAGE_BYTES, src, B_STAGE_BYTES, &full[s], kMask);
+              }
             }
+            __syncwarp();
           }
       }
     } else if (warp == 1) {
       // ===== MMA issuer ======================================================================================
-      if (lane == 0) {
+      {   // warp-uniform loops, one elected lane issues
         if (fuse1) {   // hidden = A0' x W1'^T into an accumulator buffer, then wait for the epilogue to turn it into A'
           const uint32_t buf = ma & 1, aph = (ma >> 1) & 1;
           mbar_wait(&tempty[buf], aph ^ 1);
@@ -272,13 +286,16 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
             mbar_wait(&full[s], ph);
             tc_fence_after();
             const uint32_t a0 = smem_u32(sA + (size_t)kb * A_KB_BYTES), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)
-              umma_bf16(d, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc1, (kb | kk) != 0);
-            if constexpr (CL == 1) umma_commit(&empty[s]);
-            else umma_commit_mcast(&empty[s], kMask);
+              for (int kk = 0; kk < BK / 16; ++kk)
+                umma_bf16(d, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc1, (kb | kk) != 0);
+              if constexpr (CL == 1) umma_commit(&empty[s]);
+              else umma_commit_mcast(&empty[s], kMask);
+              if (kb == p.n_kb1 - 1) umma_commit(&tfull[buf]);
+            }
+            __syncwarp();
           }
-          umma_commit(&tfull[buf]);
           ++ma;
           mbar_wait(a_ready, mtc & 1);
           tc_fence_after();
@@ -293,13 +310,16 @@ __global__ void __launch_bounds__(THREADS, 1) radial_gemm_kernel(const GemmParam
             mbar_wait(&full[s], ph);
             tc_fence_after();
             const uint32_t a0 = smem_u32(sA + (size_t)kb * A_KB_BYTES), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)
-              umma_bf16(d, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kb | kk) != 0);
-            if constexpr (CL == 1) umma_commit(&empty[s]);     // stage free once these MMAs have read it
-            else umma_commit_mcast(&empty[s], kMask);          // ... signalled to every CTA of the cluster
+              for (int kk = 0; kk < BK / 16; ++kk)
+                umma_bf16(d, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kb | kk) != 0);
+              if constexpr (CL == 1) umma_commit(&empty[s]);     // stage free once these MMAs have read it
+              else umma_commit_mcast(&empty[s], kMask);          // ... signalled to every CTA of the cluster
+              if (kb == p.n_kb - 1) umma_commit(&tfull[buf]);    // accumulator complete
+            }
+            __syncwarp();
           }
-          umma_commit(&tfull[buf]);     // accumulator complete
         }
       }
     } else if (warp >= 4) {

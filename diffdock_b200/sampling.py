@@ -117,6 +117,25 @@ def crop_receptor(g, cutoff):
     return out
 
 
+_GRAPH_POOLS = {}
+
+
+def _graph_pool(device):
+    """Memory pool shared by the step graphs of one device.  torch releases a graph pool when the last graph captured into it
+    dies, so a one-kernel anchor graph keeps it alive for the life of the process."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _GRAPH_POOLS:
+        pool = torch.cuda.graph_pool_handle()
+        anchor = torch.cuda.CUDAGraph()
+        scratch = torch.zeros(8, device=dev)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(anchor, pool=pool):
+            scratch.add_(1.0)
+        _GRAPH_POOLS[key] = (pool, anchor, scratch)
+    return _GRAPH_POOLS[key][0]
+
+
 class GraphedSteps:
     """All reverse-diffusion steps of one batch as replays of ONE CUDA graph.
 
@@ -158,10 +177,22 @@ class GraphedSteps:
 
         pos0 = self.pos.clone()
         # Outside the capture: the per-batch constants (receptor embedding, static CSR; they read sizes back to the host)
-        # and, the first time a model is used, one eager step (lazy library handles, kernel attributes, table uploads).
+        # and, the first time a model meets a batch of these shapes, one eager step: lazy library handles, table uploads,
+        # and above all lazy module loading - a kernel variant (cuBLAS picks them by shape, the conv kernel has a single-CTA
+        # and a CTA-pair form) that runs for the first time INSIDE a capture invalidates it.
         if hasattr(model, '_static'):
             model._static(g)
-        n_warm = warmup if not getattr(model, '_graph_warmed', False) else 0
+        sig = (b, n_lig, n_rec, int(g['ligand', 'ligand'].edge_index.shape[1]), int(g['receptor', 'receptor'].edge_index.shape[1]),
+               int(bond_u.shape[0]) if bond_u is not None else 0, draw_noise, philox is not None)
+        seen = getattr(model, '_graph_warmed_shapes', None)
+        if seen is None:
+            seen = set()
+            try:
+                model._graph_warmed_shapes = seen
+            except Exception:
+                pass
+        n_warm = 0 if sig in seen else warmup
+        seen.add(sig)
         if n_warm:
             side = torch.cuda.Stream(device=device)
             side.wait_stream(torch.cuda.current_stream(device))
@@ -173,8 +204,12 @@ class GraphedSteps:
                 model._graph_warmed = True
             except Exception:
                 pass
+        # One memory pool per device shared by all step graphs of this process: a sampling() call captures a new graph per
+        # batch (shapes differ from complex to complex); with a private pool each capture would cudaMalloc its whole
+        # footprint again (hundreds of ms for a 1500-residue x 40-pose batch) - the blocks of a finished batch's graph are
+        # reused instead.
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=_graph_pool(device)):
             one_step()
         self.pos.copy_(pos0)
         self.step.zero_()

@@ -57,7 +57,7 @@ def test_graph_fill_static_edges_first_and_caps(built_lib):
     """Ligand graph: bond edges (CSR by target) listed before the radius hits, self excluded, cap 32 (+ self)."""
     from diffdock_b200 import ops
     sizes = [40, 25]
-    x, _, bx, _ = _cloud(2, sizes, [1], spread=2.5)                # dense: the cap binds for many atoms
+    x, _, bx, _ = _cloud(2, sizes, [1], spread=1.2)                # dense: the cap binds for many atoms
     n = x.shape[0]
     B = len(sizes)
     ptr = ops.segment_ptr(bx, B)
@@ -70,7 +70,7 @@ def test_graph_fill_static_edges_first_and_caps(built_lib):
     pre_ptr, pre_col, pre_cnt32 = pre_ptr.cuda(), pre_col.cuda(), pre_cnt.int().cuda()
     bx32 = bx.int().contiguous()
     centre, nbr, cnt = ops.radius(x, x, ptr, bx, r=5.0, max_num_neighbors=33, exclude_self=True)
-    assert int(cnt.max()) == 32
+    assert int(cnt.max()) in (32, 33)          # the cap binds (33 when the atom itself is not among its first 33 hits)
     tot = ops.radius_count(x, x, ptr, bx32, r=5.0, max_num_neighbors=33, exclude_self=True) + pre_cnt32
     incl = torch.cumsum(tot, 0, dtype=torch.int32)
     E = int(incl[-1])

@@ -79,7 +79,7 @@ if __name__ == '__main__':
             for n_l in (20, 40, 80):
                 n_nodes = 32 * (n_r + n_l)
                 E = min(32 * (24 * n_r), 400000)          # receptor contact edges of a 32-pose batch, capped by memory
-                r = run(E, n_nodes, 24, 512, 0, 0)
+                r = run(E, n_nodes, 24, 768, 0, 0)          # 3 KB chunks: the default of build_table / bench.py
                 r.update(n_res=n_r, n_lig=n_l, frac=round(r['GBps'] / peak, 3))
                 print(json.dumps(r), flush=True)
     else:

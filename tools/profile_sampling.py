@@ -32,7 +32,7 @@ if __name__ == '__main__':
                     **bench.model_kwargs(args)).eval().to(dev)
     sched = get_t_schedule('expbeta', 20)
     out = {}
-    for rep in range(3):
+    for rep in range(4):
         poses = make_pose_list(a.poses, n_res=a.n_res, n_atoms=a.n_atoms, seed=5 + rep, tr_sigma_max=args.tr_sigma_max,
                                share_receptor=bool(a.share))
         marks = {}
@@ -47,6 +47,8 @@ if __name__ == '__main__':
                 marks[name] = marks.get(name, 0.0) + time.perf_counter() - t0
                 return r
             return w
+        orig_static = model._static
+        model._static = timed('static', orig_static)
         S._collate_any = timed('collate+h2d', orig_collate)
         S.GraphedSteps.__init__ = timed('static+capture', orig_init)
         S.GraphedSteps.run = timed('replays', orig_run)
@@ -58,5 +60,6 @@ if __name__ == '__main__':
         torch.cuda.synchronize()
         marks['total'] = time.perf_counter() - t0
         S._collate_any, S.GraphedSteps.__init__, S.GraphedSteps.run = orig_collate, orig_init, orig_run
+        del model._static
         out[f'rep{rep}'] = {k: round(v * 1e3, 1) for k, v in marks.items()}
     print(json.dumps(out))
