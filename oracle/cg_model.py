@@ -226,7 +226,9 @@ class CGModel(nn.Module):
                     ea_ = [ea_[:s1], ea_[s1:s2]]
                 node = layer(node, ei[:, :s2], ea_, sh[:s2], edge_weight=ew[:s2])
         lig_node = node[:n_lig]
+        return self._heads(data, lig_node, tr_sigma, rot_sigma, tor_sigma)
 
+    def _heads(self, data, lig_node, tr_sigma, rot_sigma, tor_sigma):   # cg_model.py:368-424 (shared with aa_model.py:443-508)
         # translation / rotation head
         c_ei, c_ea, c_sh = self.build_center_conv_graph(data)
         c_ea = self.center_edge_embedding(c_ea)

@@ -142,19 +142,26 @@ def load_golden(name):
     return torch.load(_os.path.join(GOLDEN, name), weights_only=False)
 
 
-def golden_model(case, which):
-    """Model ('oracle' on CPU | 'product' on cuda:0) + pose list rebuilt from a ref_cg_model.pt case."""
+def golden_model(case, which, all_atoms=False):
+    """Model ('oracle' on CPU | 'product' on cuda:0) + pose list rebuilt from a ref_cg_model.pt case (``all_atoms``: a
+    ref_aa_model.pt case, models/aa_model.py)."""
     from argparse import Namespace
     from functools import partial
     from diffdock_b200.hetero import graph_from_dict
     a = Namespace(**case['args'])
     if which == 'oracle':
-        from oracle.cg_model import CGModel
+        if all_atoms:
+            from oracle.aa_model import AAModel as CGModel
+        else:
+            from oracle.cg_model import CGModel
         from oracle.layers import get_timestep_embedding
         from oracle.diffusion import t_to_sigma
         dev = 'cpu'
     else:
-        from diffdock_b200.cg_model import CGModel
+        if all_atoms:
+            from diffdock_b200.aa_model import AAModel as CGModel
+        else:
+            from diffdock_b200.cg_model import CGModel
         from diffdock_b200.diffusion_utils import get_timestep_embedding, t_to_sigma
         dev = torch.device('cuda:0')
     m = CGModel(partial(t_to_sigma, args=a), dev, get_timestep_embedding('sinusoidal', 8, a.embedding_scale),

@@ -208,3 +208,23 @@ def test_fourier_time_embedding_matches_reference_fixture():
         emb = make('fourier', ref['dim'], ref['scale'])
         assert torch.equal(emb.W, ref['W']) and list(emb.state_dict().keys()) == ['W']
         assert float((emb(ref['x']) - ref['out']).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_oracle_all_atom_score_model_matches_reference_fixture(idx):
+    """oracle/aa_model.py vs the unmodified models/aa_model.py (tests/golden/make_golden_aa_model.py): nine edge groups over
+    ligand atoms, residues and receptor atoms (lmax 2; lmax 1 with one shared radial MLP; protein embedding layer)."""
+    import copy
+    from diffdock_b200.hetero import collate
+    from oracle.diffusion import set_time
+    from tests.parity_helpers import golden_model, load_golden
+    case = load_golden('ref_aa_model.pt')[idx]
+    m, poses, a = golden_model(case, 'oracle', all_atoms=True)
+    b = collate(copy.deepcopy(poses))
+    t = case['t']
+    set_time(b, t, t, t, len(poses), 'cpu', all_atoms=True)
+    with torch.no_grad():
+        tr, rot, tor, _ = m(b)
+    for got, key in ((tr, 'tr'), (rot, 'rot'), (tor, 'tor')):
+        ref = case[key]
+        assert got.shape == ref.shape and float((got - ref).abs().max() / ref.abs().max()) < 1e-5
