@@ -415,11 +415,43 @@ class CGModel(nn.Module):
             (rl_tgt, rl_src, lr_ea, lr_vec, lr_ew, dict(n_edges_dev=lr_n, edge_perm=rl_perm, vec_sign=-1.0)),   # rec <- lig
         ]
         L = len(self.conv_layers)
+        shared = self._shared_receptor_messages(data, c, rec, rec_node, sig, n_lig) if L > 1 else None
         for l, layer in enumerate(self.conv_layers):
             use = groups if l < L - 1 else groups[:2]       # last layer: only edges that end on ligand atoms (:347-349)
-            node = layer.forward_groups(node, use, gather_scalars=ns)
+            if l == 0 and shared is not None:               # receptor <- receptor messages of layer 0: computed once per complex
+                node = layer.forward_groups(node, [use[0], use[1], None, use[3]], gather_scalars=ns, init=shared)
+            else:
+                node = layer.forward_groups(node, use, gather_scalars=ns)
         lig_node = node[:n_lig]
         return self._heads(data, c, lig_node, tr_sigma, rot_sigma, tor_sigma, sync_free=True)
+
+    def _shared_receptor_messages(self, data, c, rec, rec_node, sig, n_lig):
+        """Layer-0 receptor<-receptor messages when the batch holds B poses of ONE complex at ONE diffusion time: the residue
+        features entering the first interaction layer (static embedding + sigma embedding) and the contact graph are then the
+        same in every copy, so the messages are computed for one copy (E/B edges) and added to all copies' accumulators.
+        The reference recomputes them per pose (models/cg_model.py:342-349 over the B-fold receptor).  Needs the sampler's
+        promise that all graphs of the batch share t (``data._uniform_t``; the model API allows per-graph times)."""
+        uniq = getattr(rec, '_unique', None)
+        if uniq is None or not getattr(data, '_uniform_t', False) or not self.differentiate_convolutions:
+            return None
+        n1, e1, B = uniq
+        if B < 2 or n1 * B != rec_node.shape[0] or c['rr_tgt'].shape[0] != e1 * B:
+            return None
+        layer = self.conv_layers[0]
+        if 'rr0' not in c:          # copy 0 of the CSR-sorted contact graph (targets of copy 0 sort first), local numbering
+            i32 = lambda t: t.to(torch.int32).contiguous()
+            c['rr0'] = (i32(c['rr_tgt'][:e1]), i32(c['rr_src'][:e1]), c['rr_ea'][:e1].contiguous(), c['rr_vec'][:e1].contiguous(),
+                        c['rr_ew'][:e1].reshape(-1).contiguous() if c['rr_ew'] is not None else None)
+        t0, s0, ea0, vec0, ew0 = c['rr0']
+        zero_idx = c.setdefault('rr0_zero', torch.zeros(e1, dtype=torch.int32, device=ea0.device))
+        g0 = (t0, s0, ea0, vec0, ew0, dict(ea_add=sig[:1].contiguous(), ea_add_idx=zero_idx))
+        sum0, cnt0 = layer.accumulate_group(rec_node[:n1], g0, 2, n1, gather_scalars=self.ns)
+        N = n_lig + rec_node.shape[0]
+        sum_buf = torch.zeros((N, layer.out_size), dtype=torch.float32, device=sum0.device)
+        cnt_buf = torch.zeros((N,), dtype=torch.float32, device=sum0.device)
+        sum_buf[n_lig:].view(B, n1, layer.out_size).add_(sum0.unsqueeze(0))
+        cnt_buf[n_lig:].view(B, n1).add_(cnt0.unsqueeze(0))
+        return sum_buf, cnt_buf
 
     def _cross_edge_embedding(self, node_sigma_emb, vec, row, n_dev):
         """cross_edge_embedding(cat[sigma_emb[lig], RBF(d)]) (models/cg_model.py:326,553-554): the sigma half of the first

@@ -145,7 +145,9 @@ class GraphedSteps:
     launches (about 500 kernel launches each) with the host idle."""
 
     def __init__(self, model, g, b, coef_rows, t_rows, bond_u, bond_v, mask_u8, use_torsion, device, draw_noise,
-                 philox=None, warmup=1):
+                 philox=None, warmup=1, consume_warmup=False):
+        """``consume_warmup``: when a batch of new shapes needs an eager step before the capture, that step IS step 0 of the
+        run (``steps_done`` = 1 afterwards) instead of being thrown away - ``run(n)`` then replays the remaining n - 1."""
         self.g, self.b, self.device = g, b, device
         lig = g['ligand']
         self.pos = lig.pos = lig.pos.float().contiguous().clone()         # static buffer, updated in place
@@ -160,6 +162,7 @@ class GraphedSteps:
             for nt, n in (('ligand', n_lig), ('receptor', n_rec)):
                 g[nt].node_t = {k: t[i].expand(n) for i, k in enumerate(names)}
             g.complex_t = {k: t[i].expand(b) for i, k in enumerate(names)}
+            g._uniform_t = True                      # every graph of the batch is at the same diffusion time
             tr, rot, tor = model(g)[:3]
             tr, rot, tor = _nan_guard(tr, rot, tor)
             has_tor = use_torsion and tor is not None and tor.numel() > 0
@@ -193,6 +196,7 @@ class GraphedSteps:
                 pass
         n_warm = 0 if sig in seen else warmup
         seen.add(sig)
+        self.steps_done = 0
         if n_warm:
             side = torch.cuda.Stream(device=device)
             side.wait_stream(torch.cuda.current_stream(device))
@@ -211,12 +215,14 @@ class GraphedSteps:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, pool=_graph_pool(device)):
             one_step()
-        self.pos.copy_(pos0)
-        self.step.zero_()
+        if pos0 is not None:                    # the capture itself executes nothing; undo the discarded warm-up
+            self.pos.copy_(pos0)
+            self.step.zero_()
 
     def run(self, n_steps):
-        for _ in range(n_steps):
+        for _ in range(n_steps - self.steps_done):
             self.graph.replay()
+        self.steps_done = n_steps
         return self.pos
 
 
@@ -259,6 +265,7 @@ def _eager_steps(g, b, model, inference_steps, tr_schedule, rot_schedule, tor_sc
             mod = g
         set_time(mod, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b,
                  bool(getattr(model_args, 'all_atoms', False)), device)
+        mod._uniform_t = True                        # set_time gives every graph of the batch the same diffusion time
         tr_score, rot_score, tor_score = model(mod)[:3]
         tr_score, rot_score, tor_score = _nan_guard(tr_score, rot_score, tor_score)
         has_tor = use_torsion and tor_score.numel() > 0
@@ -341,7 +348,8 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             t_rows.append([float(tr_schedule[t_idx]), float(rot_schedule[t_idx]), float(tor_schedule[t_idx])])
         if graphed and t_schedule is None and b > 0:
             steps = GraphedSteps(model, g, b, coef_rows, t_rows, bond_u, bond_v, mask_u8, use_torsion, device,
-                                 draw_noise=not (ode or no_random), philox=(seed, keys) if philox else None)
+                                 draw_noise=not (ode or no_random), philox=(seed, keys) if philox else None,
+                                 consume_warmup=True)
             steps.run(inference_steps)
         else:
             _eager_steps(g, b, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_schedule, t_to_sigma,

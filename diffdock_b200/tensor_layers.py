@@ -285,13 +285,15 @@ class TensorProductConvLayer(nn.Module):
                          residual=residual).to(_dtype)
 
     @torch.no_grad()
-    def forward_groups(self, node_attr, groups, out_nodes=None, reduce='mean', gather_scalars=0):
+    def forward_groups(self, node_attr, groups, out_nodes=None, reduce='mean', gather_scalars=0, init=None):
         """Fast internal entry (used by diffdock_b200.CGModel): ``groups`` is a list with one item per radial MLP of this
         layer, each ``(tgt_int32, src_int32, edge_attr, edge_vec, edge_weight | None[, extras])`` already CSR-sorted by
         target, so that no per-layer concatenation / conversion / slicing of the edge arrays is needed.  ``extras`` (dict)
         carries the indirections of the fused kernel - ``n_edges_dev`` (live edge count in device memory, the arrays are
         upper-bound buffers), ``edge_perm``, ``vec_sign``, ``ea_add`` / ``ea_add_idx`` (diffdock_b200/fused.py:fused_conv) -
-        and requires a layer shape the fused kernel supports."""
+        and requires a layer shape the fused kernel supports.  A ``None`` entry skips that group's radial MLP;
+        ``init = (sum [n_out, D_out], cnt [n_out])`` are accumulators the layer starts from instead of zeros (messages
+        computed elsewhere, see ``accumulate_group``)."""
         x = node_attr.float()
         if x.stride(1) != 1:
             x = x.contiguous()
@@ -299,12 +301,25 @@ class TensorProductConvLayer(nn.Module):
         scale, shift = self.batch_norm.fold() if self.batch_norm is not None else (None, None)
         fcs = [self.fc] * len(groups) if self.edge_groups == 1 else list(self.fc)
         prepared = [g if (g is not None and g[0].shape[0] > 0) else None for g in groups]
-        if all(g is None for g in prepared):
+        if all(g is None for g in prepared) and init is None:
             out = torch.zeros((x.shape[0], self.out_size), dtype=torch.float32, device=x.device)
             if self.residual:
                 out[:, :x.shape[1]] += x
             return out
-        return self._run(x, prepared, fcs, True, 1.0, n_out, reduce, gather_scalars, scale, shift)
+        return self._run(x, prepared, fcs, True, 1.0, n_out, reduce, gather_scalars, scale, shift, init=init)
+
+    @torch.no_grad()
+    def accumulate_group(self, node_attr, group, group_index, n_out, gather_scalars=0):
+        """Raw accumulators ``(sum [n_out, D_out], cnt [n_out])`` of ONE edge group (radial MLP ``group_index`` of this layer)
+        without the mean / BatchNorm / residual epilogue - for messages that are shared by several target blocks (the
+        receptor<-receptor messages of the first interaction layer are identical for all poses of a complex) and are added to
+        the layer's accumulators through ``forward_groups(..., init=...)``."""
+        x = node_attr.float()
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        fcs = [self.fc] if self.edge_groups == 1 else list(self.fc)
+        fc = fcs[0] if self.edge_groups == 1 else fcs[group_index]
+        return self._run(x, [group], [fc], True, 1.0, int(n_out), 'sum', gather_scalars, None, None, finalize=False)
 
     def fused_capable(self, k_edge, gather_scalars):
         """True if every radial MLP of this layer runs on the fully fused kernel for ``k_edge`` per-edge attribute columns
@@ -316,11 +331,16 @@ class TensorProductConvLayer(nn.Module):
         k_in = k_edge + 2 * gather_scalars
         return all(fused.ENABLED and self._fusable(fc, k_in) and fused.supported(table, fc[0].out_features, k_in) for fc in fcs)
 
-    def _run(self, x, prepared, fcs, from_vec, ew_scalar, n_out, reduce, gather_scalars, scale, shift, residual=None):
+    def _run(self, x, prepared, fcs, from_vec, ew_scalar, n_out, reduce, gather_scalars, scale, shift, residual=None,
+             init=None, finalize=True):
         handle = self.tp.handle(from_vec)
         table = handle.table
-        sum_buf = torch.zeros((n_out, self.out_size), dtype=torch.float32, device=x.device)
-        cnt_buf = torch.zeros((n_out,), dtype=torch.float32, device=x.device)
+        if init is not None:
+            sum_buf, cnt_buf = init
+            assert tuple(sum_buf.shape) == (n_out, self.out_size) and sum_buf.is_contiguous() and cnt_buf.shape[0] == n_out
+        else:
+            sum_buf = torch.zeros((n_out, self.out_size), dtype=torch.float32, device=x.device)
+            cnt_buf = torch.zeros((n_out,), dtype=torch.float32, device=x.device)
         blk = None
         for item, fc in zip(prepared, fcs):
             if item is None:
@@ -355,6 +375,8 @@ class TensorProductConvLayer(nn.Module):
                 ops.tpconv_accumulate(handle, x, src32[b0:b1], tgt32[b0:b1], geo[b0:b1], w, sum_buf, cnt_buf,
                                       edge_weight=ew[b0:b1] if ew is not None else None, count_node_bytes=b0 == 0)
                 del w
+        if not finalize:
+            return sum_buf, cnt_buf
         res = x if (self.residual if residual is None else residual) else None
         return ops.tpconv_finalize(sum_buf, cnt_buf, reduce == 'mean', scale, shift, res)
 
