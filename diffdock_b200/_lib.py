@@ -36,6 +36,8 @@ SIGNATURES = {
                                  _i64, _vp]),
     'ddb200_fused_conv': (_int, [_vp, _vp]),          # (const ddb200_fused_args*, stream)
     'ddb200_fused_debug_read': (_int, [_vp]),
+    'ddb200_contact_count': (_int, [_vp, _i32, C.c_float, _i32, _i32, _vp, _vp]),
+    'ddb200_contact_fill': (_int, [_vp, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -242,6 +242,22 @@ int ddb200_fused_conv(const ddb200_fused_args* args, void* stream);
  * counters per warp role; this copies the 32 counters to `out` (host, uint64_t[32]) and clears them.  DDB200_EINVAL when disabled. */
 int ddb200_fused_debug_read(uint64_t* out);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Input side: receptor contact graph (residues or atoms of ONE complex) on the device, two passes around the caller's
+ * exclusive scan of `count` (as ddb200_radius_count / _fill).  For every centre i over pos [n, 3]:
+ *   hits = { j != i : d(i, j) < cutoff }        d = torch.cdist(pos, pos)[i, j], reproduced bit for bit in fp32
+ *   |hits| <= max_neighbors : the hits in ascending index order
+ *   |hits| >  max_neighbors : the max_neighbors nearest points, ascending (distance, index)
+ *   |hits| == 0             : the nearest other point
+ *   knn_only != 0           : the max_neighbors nearest points regardless of cutoff (knn_graph)
+ * out_nbr / out_ctr [E] = edge_index[0] / edge_index[1] ([neighbour, centre], centre by centre).
+ * Replaces: the cdist + Python loop of datasets/process_mols.py:168-192 (residues) and :205-224 (atoms).
+ * ------------------------------------------------------------------------------------------------------------- */
+int ddb200_contact_count(const float* pos, int32_t n, float cutoff, int32_t max_neighbors, int32_t knn_only,
+                         int32_t* count, void* stream);
+int ddb200_contact_fill(const float* pos, int32_t n, float cutoff, int32_t max_neighbors, int32_t knn_only,
+                        const int32_t* row_start, int32_t* out_nbr, int32_t* out_ctr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

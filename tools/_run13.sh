@@ -1,6 +1,7 @@
 set -x
-timeout 1200 python -m pytest tests/test_sync_free_gpu.py tests/test_sampler_gpu.py tests/test_model_gpu.py tests/test_full_size_gpu.py -q 2>&1 | tail -8
-timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02k_bench.json 2> gpurun_out/r02k_bench.err
-tail -3 gpurun_out/r02k_bench.err
-python -c "
-import json;d=json.load(open('gpurun_out/r02k_bench.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['e2e']['runs_s'],d['config2_batch32'],d['cfg_l1_sh_lmax1'],d['roofline']['frac'],d['roofline']['tensor']['issued_TFLOPs'])"
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 ) > gpurun_out/r02k_pytest_gpu.txt 2>&1; cat gpurun_out/r02k_pytest_gpu.txt
+DDB200_FUSED_DEBUG=1 timeout 300 python tools/bench_fused.py > gpurun_out/r02k_fused_dbg.json 2>&1; cat gpurun_out/r02k_fused_dbg.json
+timeout 300 python tools/bench_fused.py > gpurun_out/r02k_fused.json 2>&1; cat gpurun_out/r02k_fused.json
+timeout 300 python tools/bench_fused.py --edges 1600000 --nodes 70000 > gpurun_out/r02k_fused_1m6.json 2>&1; cat gpurun_out/r02k_fused_1m6.json
+( time timeout 900 python bench.py ) > gpurun_out/r02k_bench.json 2> gpurun_out/r02k_bench.err; tail -4 gpurun_out/r02k_bench.err; cut -c1-600 gpurun_out/r02k_bench.json
