@@ -9,7 +9,7 @@ embeddings, 6 tensor-product conv layers, tr/rot/tor heads) -> pose update, for 
 (1500 residues / 40 ligand atoms; 40 poses = BASELINE config 3, the full sampling loop) per GPU; consecutive steps walk
 the 20-step 'expbeta' schedule (t: 1 -> 0.05), so K=20 is exactly one sampling run.  value = total poses / (20 * mean step
 time), steps launched as replays of the sampler's CUDA graph (diffdock_b200.sampling.GraphedSteps), inputs resident.
-The JSON line also carries: the end-to-end number through diffdock_b200.sampling.sampling() with host inputs (median of 3
+The JSON line also carries: the end-to-end number through diffdock_b200.sampling.sampling() with host inputs (median of 5
 calls after one warm call), the same measurement for BASELINE config 2 (batch 32) and for the sh_lmax=1 model (CFG-L1), the
 roofline of the fused tensor-product conv kernel on ALGORITHMIC work (SURVEY 8(d) bytes and fp32 FLOPs per edge) next to
 the issued tensor-pipe rate, measured live with CUDA events, the parity of the timed workload against the CPU oracle, and
@@ -338,7 +338,7 @@ class Workload:
     def step(self, i):
         (self.graph_step if self.graphed is not None else self.eager_step)(i)
 
-    def e2e(self, host_list, repeats=3):
+    def e2e(self, host_list, repeats=5):
         """sampling() from pinned host inputs to host outputs: median wall time of `repeats` calls after one warm call."""
         from diffdock_b200.sampling import sampling
         times, final = [], None
@@ -517,7 +517,7 @@ def run_cuda(cli):
                 "config": workload_config(cli, cli.poses), "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "poses/s", "h2d_bytes_per_step": h2d // N_SCHED,
                         "d2h_bytes_per_step": int(final.numel() * 4 // N_SCHED), "seconds_per_run": e2e_max,
-                        "runs_s": e2e_all, "how": "median of 3 sampling() calls after one warm call; each call collates the "
+                        "runs_s": e2e_all, "how": "median of 5 sampling() calls after one warm call; each call collates the "
                                                   "host poses, uploads one receptor copy + all ligands, captures the step graph, "
                                                   "replays it 20 times and copies the final coordinates back"},
                 "gpu_launches": int(round(launches_per_step * cli.steps)), "launches_per_step": launches_per_step,

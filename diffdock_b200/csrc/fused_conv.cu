@@ -46,7 +46,7 @@ constexpr int MAX_KB = 5;                        // k-blocks of either operand i
 constexpr int MAX_KA = MAX_KB;
 constexpr int OPS_PER_KB = 8;                    // MMAs that read one staged k-block of B (4 steps x up to 2 A partners)
 constexpr int THREADS = 256;
-constexpr int MAX_TILES = 160, MAX_PATHS = 16, MTAB = 48;     // per path: dense [3][3][5] table, padded to 48 floats
+constexpr int MAX_TILES = 128, MAX_PATHS = 16, MTAB = 48;     // per path: dense [3][3][5] table, padded to 48 floats
 constexpr int FLUSH_LD = 33;                     // padded row of the per-warp scatter staging buffer [48][33]
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,24 +147,43 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // holds N/2 rows of B.
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+// All MMAs that read one staged k-block of B, in ONE asm block: up to OPS_PER_KB tcgen05.mma, each guarded by a predicate
+// (op word 1 == 0xFFFFFFFF: no MMA in this slot).  a[i] = low descriptor word of the A operand (absolute), w[i] = offset of
+// the B step inside the stage (16-byte units), b_base = low descriptor word of the stage.  Issued as straight-line code the
+// instruction descriptor and the accumulator address are moved to uniform registers once per k-block, and a slot costs an
+// add, two register->uniform moves and the MMA (the branchy one-MMA-per-asm form cost ~14 instructions per MMA and made
+// the issuing thread, not the tensor pipe, the limit: 76 clk per MMA measured against 87 clk of tensor work).
 template <int CG>
-__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
-  if constexpr (CG == 1)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI)
-        : "memory");
+__device__ __forceinline__ void umma_stage(uint32_t tmem_d, uint32_t idesc, uint32_t accum0, uint32_t b_base,
+                                           const uint32_t (&a)[OPS_PER_KB], const uint32_t (&w)[OPS_PER_KB]) {
+#define DDB200_MMA_SLOT(CGS, I, AI, WI, PACC)                                        \
+  "setp.ne.u32 q, " WI ", 0xFFFFFFFF;\n\t"                                            \
+  "add.u32 t, %3, " WI ";\n\t"                                                        \
+  "mov.b64 da, {" AI ", %4};\n\t"                                                     \
+  "mov.b64 db, {t, %4};\n\t"                                                          \
+  "@q tcgen05.mma.cta_group::" CGS ".kind::f16 [%0], da, db, %1, " PACC ";\n\t"
+#define DDB200_MMA_STAGE(CGS)                                                         \
+  asm volatile(                                                                       \
+      "{\n\t.reg .pred p0, pt, q;\n\t.reg .b64 da, db;\n\t.reg .b32 t;\n\t"           \
+      "setp.ne.b32 p0, %2, 0;\n\t"                                                    \
+      "setp.eq.u32 pt, 0, 0;\n\t"                                                     \
+      DDB200_MMA_SLOT(CGS, 0, "%5", "%13", "p0")                                      \
+      DDB200_MMA_SLOT(CGS, 1, "%6", "%14", "pt")                                      \
+      DDB200_MMA_SLOT(CGS, 2, "%7", "%15", "pt")                                      \
+      DDB200_MMA_SLOT(CGS, 3, "%8", "%16", "pt")                                      \
+      DDB200_MMA_SLOT(CGS, 4, "%9", "%17", "pt")                                      \
+      DDB200_MMA_SLOT(CGS, 5, "%10", "%18", "pt")                                     \
+      DDB200_MMA_SLOT(CGS, 6, "%11", "%19", "pt")                                     \
+      DDB200_MMA_SLOT(CGS, 7, "%12", "%20", "pt")                                     \
+      "}"                                                                             \
+      ::"r"(tmem_d), "r"(idesc), "r"(accum0), "r"(b_base), "r"(DESC_HI),              \
+        "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),   \
+        "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])   \
+      : "memory")
+  static_assert(OPS_PER_KB == 8, "umma_stage is written for 8 slots");
+  if constexpr (CG == 1) DDB200_MMA_STAGE("1"); else DDB200_MMA_STAGE("2");
+#undef DDB200_MMA_STAGE
+#undef DDB200_MMA_SLOT
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -315,21 +334,24 @@ __device__ __forceinline__ void tile_body(uint32_t taddr, int nch, float* xn, in
 
 // MMA schedule of one staged k-block of B (4 steps of 16 columns; images [hi | lo | bias], S = Kp / 16 steps per part):
 // step c < S (hi): x A hi (column block c) and x A lo (block S + c);  S <= c < 2S (lo): x A hi (block c - S);
-// c == 2S (bias): x A ones (block 2S).  An op word = A descriptor offset (16-byte units) | B step within the k-block << 28;
-// 0xFFFFFFFF terminates the list.
+// c == 2S (bias): x A ones (block 2S).  Per k-block OPS_PER_KB slots of two words, stored as [A words 0-7 | B words 0-7]:
+// A word = low descriptor word of the A column block (absolute), B word = offset of the B step inside the stage in 16-byte
+// units, 0xFFFFFFFF = empty slot.
 __device__ __forceinline__ uint32_t a_block_offset(int c) { return (uint32_t)((c >> 2) * (A_KB_BYTES >> 4) + (c & 3) * 2); }
-__device__ __forceinline__ void build_ops(uint32_t* ops, int S) {     // ops[MAX_KB][OPS_PER_KB]
+__device__ __forceinline__ void build_ops(uint32_t* ops, int S, uint32_t a_lo0) {     // ops[MAX_KB][2][OPS_PER_KB]
   for (int kb = 0; kb < MAX_KB; ++kb) {
+    uint32_t* oa = ops + kb * 2 * OPS_PER_KB;
+    uint32_t* ob = oa + OPS_PER_KB;
     int n = 0;
     for (int j = 0; j < 4; ++j) {
       const int c = kb * 4 + j;
       if (c < S) {
-        ops[kb * OPS_PER_KB + n++] = a_block_offset(c) | ((uint32_t)j << 28);
-        ops[kb * OPS_PER_KB + n++] = a_block_offset(S + c) | ((uint32_t)j << 28);
-      } else if (c < 2 * S) ops[kb * OPS_PER_KB + n++] = a_block_offset(c - S) | ((uint32_t)j << 28);
-      else if (c == 2 * S) ops[kb * OPS_PER_KB + n++] = a_block_offset(2 * S) | ((uint32_t)j << 28);
+        oa[n] = a_lo0 + a_block_offset(c); ob[n++] = (uint32_t)j * 2;
+        oa[n] = a_lo0 + a_block_offset(S + c); ob[n++] = (uint32_t)j * 2;
+      } else if (c < 2 * S) { oa[n] = a_lo0 + a_block_offset(c - S); ob[n++] = (uint32_t)j * 2; }
+      else if (c == 2 * S) { oa[n] = a_lo0 + a_block_offset(2 * S); ob[n++] = (uint32_t)j * 2; }
     }
-    for (; n < OPS_PER_KB; ++n) ops[kb * OPS_PER_KB + n] = 0xFFFFFFFFu;
+    for (; n < OPS_PER_KB; ++n) { oa[n] = a_lo0; ob[n] = 0xFFFFFFFFu; }
   }
 }
 
@@ -344,12 +366,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
   float* sFlush = sY + 9 * 128;                                  // [4 warps][48][33] scatter staging
   float* sMtab = sFlush + 4 * 48 * FLUSH_LD;                     // [MAX_PATHS][48]
   int* sTiles = reinterpret_cast<int*>(sMtab + MAX_PATHS * MTAB);   // [MAX_TILES][8]
-  uint32_t* sOps = reinterpret_cast<uint32_t*>(sTiles + MAX_TILES * 8);   // [2][MAX_KB][OPS_PER_KB] MMA schedules (16 B aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOps + 2 * MAX_KB * OPS_PER_KB);
-  uint64_t* full = bars;                 // this CTA's part of B stage s has landed (TMA complete_tx)
+  uint32_t* sOps = reinterpret_cast<uint32_t*>(sTiles + MAX_TILES * 8);   // [2][MAX_KB][2][OPS_PER_KB] MMA schedules (16 B aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOps + 2 * MAX_KB * 2 * OPS_PER_KB);
+  uint64_t* full = bars;                 // B stage s has landed: this CTA's part (TMA complete_tx) and, on the leader, the peer's
   uint64_t* empty = bars + STAGES;       // the MMAs reading stage s are done (commit; both CTAs of a pair)
-  uint64_t* pfull = bars + 2 * STAGES;   // leader only: the peer's part of stage s has landed (relayed by the peer)
-  uint64_t* tfull = bars + 3 * STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;          // leader: consumers of all CG CTAs have drained the accumulator
   uint64_t* a_ready = tempty + 2;        // leader: all CG operand images hold A'
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
@@ -360,10 +381,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
   const int S1 = p.K1p >> 4, S2 = p.Hp >> 4;
   for (int i = tid; i < p.n_tiles * 8; i += THREADS) sTiles[i] = p.tiles[i];
   for (int i = tid; i < p.n_paths * MTAB; i += THREADS) sMtab[i] = p.mtab[i];
-  if (tid == 32) build_ops(sOps, S1);
-  if (tid == 64) build_ops(sOps + MAX_KB * OPS_PER_KB, S2);
+  if (tid == 32) build_ops(sOps, S1, umma_desc_lo(smem_u32(sA)));
+  if (tid == 64) build_ops(sOps + MAX_KB * 2 * OPS_PER_KB, S2, umma_desc_lo(smem_u32(sA)));
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&pfull[s], 1); }
+    // leader of a pair: a stage is full when its own bulk copy has landed (1 arrival + transaction bytes) AND the peer has
+    // relayed the completion of its half (1 arrival): one barrier, one wait per stage in the MMA issue loop
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], (CG == 2 && leader) ? 2 : 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * CG); }
     mbar_init(a_ready, 4 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -404,66 +427,86 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
     const long long mt = unit * CG + rank;                   // may be one past the end for the peer: all rows invalid
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     const long long t_unit = DBG_T();
+    // The hidden layer's operand images do not depend on the unit: the producer warp requests them before taking part in the
+    // operand build, so the first MMA finds them in shared memory (their stages are free or about to be: the MMAs that read
+    // the previous unit's last stages were issued before the cluster barrier above and complete on their own).
+    if (warp == 0) {
+      const uint32_t sB0 = smem_u32(sB), full0 = smem_u32(full), empty0 = smem_u32(empty);
+      const uint32_t bytes = (uint32_t)(n1 / CG) * 128u;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.w1img) + (size_t)rank * bytes;
+      const int npre = p.n_kb1 < STAGES ? p.n_kb1 : STAGES;      // never more than the ring holds: nothing drains it yet
+      for (int kb = 0; kb < npre; ++kb, ++pc, src += B_IMAGE_BYTES) {
+        const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
+        mbar_wait_u32(empty0 + s * 8, ph ^ 1);
+        if (elect_one()) {
+          if (DBG && p.dbg_noload) mbar_arrive(&full[s]);
+          else {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + s * 8), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sB0 + s * B_STAGE_BYTES), "l"(src), "r"(bytes), "r"(full0 + s * 8) : "memory");
+          }
+        }
+        __syncwarp();
+      }
+    }
     // ---- A0' image: [hi | lo | 1 1 0..] of [edge_attr (+ per-graph term) | node[tgt,:ns] | node[src,:ns]] -------------
     {
       const long long e0 = mt * BM;
       const int Kin = p.K1, Kp = p.K1p;
       if (tid < BM) put_a_tail(sA, tid, Kin, Kp);
       if (((p.ne | p.ns) & 7) == 0 && ((p.ld_ea | p.ld_node) & 3) == 0) {
-        // vector path: one work item = 8 consecutive input columns of one edge = two independent 16-byte loads, two
-        // 16-byte shared stores; the index loads of all of a thread's items are issued first, then all data loads, then
-        // the conversions (one pass for K = 144: 2304 items / 256 threads = 9)
-        const int groups = Kin >> 3, items = BM * groups;
-        constexpr int PER = 9;
-        for (int base = tid; base < items; base += THREADS * PER) {
-          float4 f[PER][2];
-          long long off[PER];
-          int rr[PER], gg[PER], ai[PER];
-          const float* bp[PER];
+        // vector path: two threads per edge row, each converting a contiguous half of the row's 8-column groups (<= 9
+        // groups = 18 independent 16-byte loads).  The row's indices (attribute row, per-graph term, both end points) are
+        // loaded once per thread, then ALL data loads of the thread are issued - including the per-graph term's - then the
+        // conversions: two dependent global-memory round trips per unit (the earlier item-strided form needed an index load
+        // per group and fetched the per-graph term inside the conversion loop: three round trips, ~14 k clocks per unit).
+        const int groups = Kin >> 3, gh = (groups + 1) >> 1;
+        constexpr int PER = 9;                            // (144 / 8 + 1) / 2: Kp <= 144 (MAX_KB k-blocks)
+        const int r = tid >> 1, g0 = (tid & 1) * gh, g1 = min(groups, g0 + gh);
+        const long long e = e0 + r;
+        const bool live = e < n_edges;
+        const int ge = p.ne >> 3, gs = p.ns >> 3;           // groups of the attribute / of one node section
+        long long er = e;
+        int ai = -1, it = 0, is = 0;
+        if (live) {
+          if (g0 < ge) {
+            if (p.perm) er = (long long)__ldg(p.perm + e);
+            if (p.ea_add) ai = __ldg(p.ea_add_idx + e);
+          }
+          if (g0 < ge + gs && g1 > ge) it = __ldg(p.tgt + e);
+          if (g1 > ge + gs) is = __ldg(p.src + e);
+        }
+        const float* ea_row = p.ea + er * p.ld_ea;
+        const float* add_row = ai >= 0 ? p.ea_add + (long long)ai * p.ne : nullptr;
+        const float* t_row = p.node + (long long)it * p.ld_node - p.ne;
+        const float* s_row = p.node + (long long)is * p.ld_node - p.ne - p.ns;
+        float4 f[PER][2], ad[PER][2];
 #pragma unroll
-          for (int u = 0; u < PER; ++u) {
-            const int idx = base + u * THREADS;
-            rr[u] = -1; ai[u] = -1; off[u] = 0; bp[u] = nullptr;
-            if (idx < items) {
-              const int r = idx / groups, g = idx - r * groups, k = g << 3;
-              const long long e = e0 + r;
-              if (e < n_edges) {
-                rr[u] = r; gg[u] = g;
-                if (k < p.ne) {
-                  const long long er = p.perm ? (long long)__ldg(p.perm + e) : e;
-                  bp[u] = p.ea + k; off[u] = er * p.ld_ea;
-                  if (p.ea_add) ai[u] = __ldg(p.ea_add_idx + e);
-                } else if (k < p.ne + p.ns) {
-                  bp[u] = p.node + (k - p.ne); off[u] = (long long)__ldg(p.tgt + e) * p.ld_node;
-                } else {
-                  bp[u] = p.node + (k - p.ne - p.ns); off[u] = (long long)__ldg(p.src + e) * p.ld_node;
-                }
-              } else { rr[u] = r; gg[u] = g; }     // rows past the end: zeros
+        for (int u = 0; u < PER; ++u) {
+          const int g = g0 + u, k = g << 3;
+          f[u][0] = f[u][1] = ad[u][0] = ad[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && g < g1) {
+            const float* src = (g < ge) ? ea_row + k : (g < ge + gs ? t_row + k : s_row + k);
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            f[u][0] = __ldg(s4);
+            f[u][1] = __ldg(s4 + 1);
+            if (g < ge && add_row) {
+              const float4* a4 = reinterpret_cast<const float4*>(add_row + k);
+              ad[u][0] = __ldg(a4);
+              ad[u][1] = __ldg(a4 + 1);
             }
           }
+        }
 #pragma unroll
-          for (int u = 0; u < PER; ++u) {
-            f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bp[u]) {
-              const float4* s4 = reinterpret_cast<const float4*>(bp[u] + off[u]);
-              f[u][0] = __ldg(s4);
-              f[u][1] = __ldg(s4 + 1);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < PER; ++u) {
-            if (rr[u] >= 0) {
-              if (ai[u] >= 0) {
-                const float4* a4 = reinterpret_cast<const float4*>(p.ea_add + (long long)ai[u] * p.ne + (gg[u] << 3));
-                const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1);
-                f[u][0].x += a0.x; f[u][0].y += a0.y; f[u][0].z += a0.z; f[u][0].w += a0.w;
-                f[u][1].x += a1.x; f[u][1].y += a1.y; f[u][1].z += a1.z; f[u][1].w += a1.w;
-              }
-              uint4 hi, lo;
-              split8(reinterpret_cast<const float*>(&f[u][0]), hi, lo);
-              put_a8(sA, rr[u], gg[u] << 3, hi);
-              put_a8(sA, rr[u], Kp + (gg[u] << 3), lo);
-            }
+        for (int u = 0; u < PER; ++u) {
+          const int g = g0 + u;
+          if (g < g1) {
+            f[u][0].x += ad[u][0].x; f[u][0].y += ad[u][0].y; f[u][0].z += ad[u][0].z; f[u][0].w += ad[u][0].w;
+            f[u][1].x += ad[u][1].x; f[u][1].y += ad[u][1].y; f[u][1].z += ad[u][1].z; f[u][1].w += ad[u][1].w;
+            uint4 hi, lo;
+            split8(reinterpret_cast<const float*>(&f[u][0]), hi, lo);
+            put_a8(sA, r, g << 3, hi);
+            put_a8(sA, r, Kp + (g << 3), lo);
           }
         }
       } else {
@@ -492,20 +535,22 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
     if (tid == 0) DBG_ADD(10, DBG_T() - t_unit);
 
     if (warp == 0) {
-      // ===== operand-B producer: W1' images, then one image set per N tile ====================================
+      // ===== operand-B producer: one image set per N tile (the W1' images were requested before the operand build) ======
       // Only the rows the MMA reads (N of the tile) are fetched: images are row-major [256][128 B]; with a CTA pair this CTA
       // fetches its half of them (rows [rank * N/2, (rank + 1) * N/2) feed the accumulator columns of the same range).
       // The loop is kept lean (no divisions, 32-bit shared addresses, incremental source pointers): at ~400 clocks of MMA
       // work per stage the producer's own instruction stream is otherwise what starves the tensor pipe.
       {
         const uint32_t sB0 = smem_u32(sB), full0 = smem_u32(full), empty0 = smem_u32(empty);
-        for (int t = -1; t < p.n_tiles; ++t) {
+        const int npre = p.n_kb1 < STAGES ? p.n_kb1 : STAGES;
+        for (int t = (npre < p.n_kb1 ? -1 : 0); t < p.n_tiles; ++t) {      // t = -1: the W1' k-blocks the ring could not take
           const int nkb = (t < 0) ? p.n_kb1 : p.n_kb;
+          const int kb_first = (t < 0) ? npre : 0;
           const uint32_t bytes = (uint32_t)(((t < 0) ? n1 : sTiles[t * 8 + 1]) / CG) * 128u;
-          const unsigned char* src = ((t < 0) ? reinterpret_cast<const unsigned char*>(p.w1img)
+          const unsigned char* src = ((t < 0) ? reinterpret_cast<const unsigned char*>(p.w1img) + (size_t)kb_first * B_IMAGE_BYTES
                                               : reinterpret_cast<const unsigned char*>(p.w2img) +
                                                     (size_t)t * p.n_kb * B_IMAGE_BYTES) + (size_t)rank * bytes;
-          for (int kb = 0; kb < nkb; ++kb, ++pc, src += B_IMAGE_BYTES) {
+          for (int kb = kb_first; kb < nkb; ++kb, ++pc, src += B_IMAGE_BYTES) {
             const uint32_t s = pc % STAGES, ph = (pc / STAGES) & 1;
             const long long t0 = DBG_T();
             mbar_wait_u32(empty0 + s * 8, ph ^ 1);
@@ -556,7 +601,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
           const long long t0 = DBG_T();
           mbar_wait(&full[s], ph);
           const long long t1 = DBG_T();
-          if (elect_one()) mbar_arrive_remote_relaxed(&pfull[s], 0);
+          if (elect_one()) mbar_arrive_remote_relaxed(&full[s], 0);
           __syncwarp();
           if (lane == 0) { DBG_ADD(6, t1 - t0); DBG_ADD(7, DBG_T() - t1); }
         }
@@ -564,8 +609,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
     } else if (warp == 1) {
       // ===== MMA issuer (leader CTA of a pair only) ================================================================
       if (leader) {
-        const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), b_lo0 = umma_desc_lo(smem_u32(sB));
-        const uint32_t full0 = smem_u32(full), pfull0 = smem_u32(pfull);
+        const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB));
+        const uint32_t full0 = smem_u32(full);
         const long long t_role = DBG_T();
         long long w_te = 0, w_full = 0, w_a = 0, b_issue = 0;
         for (int t = -1; t < p.n_tiles; ++t, ++ma) {
@@ -577,24 +622,21 @@ __global__ void __launch_bounds__(THREADS, 1) fused_conv_kernel(const FusedParam
           const uint32_t d = tmem_base + buf * BN;
           const int nkb = (t < 0) ? p.n_kb1 : p.n_kb;
           const int nmma = (t < 0) ? n1 : sTiles[t * 8 + 1];
-          const uint4* ops = reinterpret_cast<const uint4*>(sOps + ((t < 0) ? 0 : MAX_KB * OPS_PER_KB));
+          const uint4* ops = reinterpret_cast<const uint4*>(sOps + ((t < 0) ? 0 : MAX_KB * 2 * OPS_PER_KB));
           const uint32_t idesc = idesc0 | ((uint32_t)(nmma >> 3) << 17);
           for (int kb = 0; kb < nkb; ++kb, ++mc) {
             const uint32_t s = mc % STAGES, ph = (mc / STAGES) & 1;
             t0 = DBG_T();
             mbar_wait_u32(full0 + s * 8, ph);
-            if constexpr (CG == 2) mbar_wait_u32(pfull0 + s * 8, ph);
             w_full += DBG_T() - t0;
             t0 = DBG_T();
             tc_fence_after();
             const uint32_t b_lo = b_lo0 + s * (B_STAGE_BYTES >> 4);
             if (elect_one()) {
-              const uint4 o0 = ops[kb * 2], o1 = ops[kb * 2 + 1];
-              const uint32_t op[OPS_PER_KB] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-#pragma unroll
-              for (int i = 0; i < OPS_PER_KB; ++i)
-                if (op[i] != 0xFFFFFFFFu)
-                  umma_bf16_lo<CG>(d, a_lo0 + (op[i] & 0x0FFFFFFFu), b_lo + (op[i] >> 28) * 2, idesc, (kb | i) != 0);
+              const uint4 a0 = ops[kb * 4], a1 = ops[kb * 4 + 1], w0 = ops[kb * 4 + 2], w1 = ops[kb * 4 + 3];
+              const uint32_t av[OPS_PER_KB] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const uint32_t wv[OPS_PER_KB] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+              umma_stage<CG>(d, idesc, (uint32_t)kb, b_lo, av, wv);
               umma_commit<CG>(&empty[s]);
               if (kb == nkb - 1) umma_commit<CG>(&tfull[buf]);
             }
@@ -873,7 +915,7 @@ extern "C" int ddb200_fused_conv(const ddb200_fused_args* a, void* stream) {
   static const int pair_env = [] { const char* e = getenv("DDB200_FUSED_CTA_PAIR"); return e ? atoi(e) : 1; }();
   const bool pair = pair_env != 0 && n_mtiles >= 2;
   const size_t fixed = (9 * 128 + 4 * 48 * FLUSH_LD + MAX_PATHS * MTAB) * 4 + MAX_TILES * 8 * 4 +
-                       2 * MAX_KB * OPS_PER_KB * 4 + 36 * sizeof(uint64_t) + 1024;
+                       2 * MAX_KB * 2 * OPS_PER_KB * 4 + 28 * sizeof(uint64_t) + 1024;
   const size_t smem = (size_t)MAX_KA * A_KB_BYTES + fixed +
                       (pair ? Ring<2>::STAGES * Ring<2>::STAGE_BYTES : Ring<1>::STAGES * Ring<1>::STAGE_BYTES);
   if (smem > 227 * 1024) return DDB200_ESMEM;

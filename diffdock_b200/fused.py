@@ -36,6 +36,7 @@ from .tp_table import TpTable
 # (mul_out, d_out) -> (consumer kind id, rows per tile)
 CONSUMER_KINDS = {(48, 1): (0, 4), (10, 3): (1, 16), (16, 1): (2, 8), (4, 3): (3, 16)}
 MAX_K = 144          # widest radial-MLP input / hidden layer (16-column sections: 2 * 144 + 16 = 304 -> 5 k-blocks of 64)
+MAX_TILES = 128      # tile table capacity of the kernel (csrc/fused_conv.cu)
 MTAB = 48            # floats per path in the dense Clebsch-Gordan table: [3][3][5] padded
 ENABLED = os.environ.get('DDB200_FUSED_CONV', '1') != '0'
 
@@ -56,7 +57,8 @@ def supported(table: TpTable, hidden: int, k1: int) -> bool:
             return False
         if (2 * p.l_in + 1) not in (1, 3) or p.l_sh > 2:
             return False
-    return True
+    n_tiles = sum(-(-p.mul_in // CONSUMER_KINDS[(p.mul_out, 2 * p.l_out + 1)][1]) for p in table.paths)
+    return n_tiles <= MAX_TILES
 
 
 def _split_images(w_rows: torch.Tensor, bias_rows: torch.Tensor, K: int):

@@ -245,9 +245,11 @@ int ddb200_fused_debug_read(uint64_t* out);
 /* ---------------------------------------------------------------------------------------------------------------
  * Input side: receptor contact graph (residues or atoms of ONE complex) on the device, two passes around the caller's
  * exclusive scan of `count` (as ddb200_radius_count / _fill).  For every centre i over pos [n, 3]:
- *   hits = { j != i : d(i, j) < cutoff }        d = torch.cdist(pos, pos)[i, j], reproduced bit for bit in fp32
+ *   hits = { j != i : d(i, j) < cutoff }        d = torch.cdist(pos, pos)[i, j]: squared distance in ATen's fp32 operation
+ *                                               order (bit-identical), correctly rounded square root
  *   |hits| <= max_neighbors : the hits in ascending index order
- *   |hits| >  max_neighbors : the max_neighbors nearest points, ascending (distance, index)
+ *   |hits| >  max_neighbors : the max_neighbors nearest points, ascending (distance, index) - np.argsort order with
+ *                             exact-distance ties (unspecified there) broken by index
  *   |hits| == 0             : the nearest other point
  *   knn_only != 0           : the max_neighbors nearest points regardless of cutoff (knn_graph)
  * out_nbr / out_ctr [E] = edge_index[0] / edge_index[1] ([neighbour, centre], centre by centre).

@@ -25,11 +25,11 @@ def _fma32(a, b, c):
     return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
 
 
-def cdist_f32(x):
-    """``torch.cdist(x, x)`` for fp32 ``x`` [N, 3] as ATen evaluates it (process_mols.py:176 calls it on the C-alpha
-    coordinates): more than 25 points -> ``_euclidean_dist``: ``[-2 x_i, |x_i|^2, 1] . [x_j, 1, |x_j|^2]`` by an sgemm with
-    K = 5, i.e. one FMA chain in k order, then clamp_min(0).sqrt(); otherwise the direct form sqrt(sum (a - b)^2).
-    tests/test_inputs_cpu.py checks bitwise equality with the installed torch."""
+def cdist_sq_f32(x):
+    """Squared distances as ``torch.cdist(x, x)`` forms them for fp32 ``x`` [N, 3] (process_mols.py:176 calls it on the
+    C-alpha coordinates).  More than 25 points -> ATen's ``_euclidean_dist``: ``[-2 x_i, |x_i|^2, 1] . [x_j, 1, |x_j|^2]``
+    by an sgemm with K = 5 - one FMA chain in k order - then clamp_min(0); otherwise the direct form sum (a - b)^2.
+    tests/test_inputs_cpu.py checks the matrix-multiply form bit for bit against the installed torch."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     n = x.shape[0]
     if n > 25:
@@ -39,12 +39,19 @@ def cdist_f32(x):
         acc = np.zeros((n, n), np.float32)
         for k in range(5):
             acc = _fma32(a[:, k:k + 1], b[None, :, k], acc)
-        return np.sqrt(np.maximum(acc, np.float32(0)))
+        return np.maximum(acc, np.float32(0))
     d = x[:, None, :] - x[None, :, :]
     acc = d[..., 0] * d[..., 0]
     acc = _fma32(d[..., 1], d[..., 1], acc)
-    acc = _fma32(d[..., 2], d[..., 2], acc)
-    return np.sqrt(acc)
+    return _fma32(d[..., 2], d[..., 2], acc)
+
+
+def cdist_f32(x):
+    """``torch.cdist(x, x)``: the correctly rounded (IEEE) fp32 square root of ``cdist_sq_f32``.  torch's CPU kernels take
+    the root with a vectorised routine that is 1 ulp off for ~0.7 % of the arguments (measured: torch 2.11, AVX-512 build) -
+    a property of the host build, not of the algorithm, so neither the oracle nor the CUDA kernel copies it; it can only
+    move a pair whose distance lies within one ulp of the cut-off."""
+    return np.sqrt(cdist_sq_f32(x))
 
 
 def contact_graph(coords, cutoff, max_neighbors=None):

@@ -202,3 +202,28 @@ def golden_confidence_model(case, which, all_atoms=False):
     m = CGOldModel(partial(t_to_sigma, args=a), dev, get_timestep_embedding('sinusoidal', 8, a.embedding_scale), **kw).eval()
     m.load_state_dict(case['state'], strict=True)
     return m.to(dev), [graph_from_dict(d) for d in case['poses']]
+
+
+def canonical_contact_edges(edge_index, coords):
+    """Contact-graph edge list [2, E] (rows [neighbour, centre], centre by centre) with TIES made canonical: where a centre's
+    neighbours are listed by distance (more hits than max_neighbors: np.argsort order, datasets/process_mols.py:184), runs of
+    exactly equal fp32 distance are re-ordered by index.  np.argsort's default sort is not stable and its tie order depends on
+    the numpy build (AVX-512 quicksort vs introsort), so that is the strongest order a restatement can reproduce."""
+    import numpy as np
+    from oracle.inputs import cdist_sq_f32
+    ei = np.asarray(edge_index)
+    sq = cdist_sq_f32(np.asarray(coords, dtype=np.float32))
+    out = ei.copy()
+    start = 0
+    E = ei.shape[1]
+    while start < E:
+        end = start
+        while end < E and ei[1, end] == ei[1, start]:
+            end += 1
+        nb = ei[0, start:end]
+        if not np.all(np.diff(nb) > 0):            # listed by distance
+            i = ei[1, start]
+            order = sorted(range(end - start), key=lambda q: (sq[i, nb[q]], nb[q]))
+            out[0, start:end] = nb[order]
+        start = end
+    return out
