@@ -263,12 +263,13 @@ def tpconv_stream_roofline(dev, n_edges=200000):
 def _ncu_traffic():
     """DRAM bytes per launch of the fused kernel from the committed ncu capture of this round (None if absent): the run
     itself cannot read dram__bytes without a profiler attached."""
-    p = os.path.join(ROOT, 'profiles', 'r02_fused_traffic.json')
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            return None
+    for name in ('r02m_fused_traffic.json', 'r02_fused_traffic.json'):        # newest capture first
+        p = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(p):
+            try:
+                return json.load(open(p))
+            except Exception:
+                return None
     return None
 
 

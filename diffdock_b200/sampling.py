@@ -21,6 +21,64 @@ from .diffusion_utils import set_time
 from .hetero import collate, collate_shared_receptor
 
 
+def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, pocket_knowledge=False, pocket_cutoff=7,
+                       initial_noise_std_proportion=-1.0, choose_residue=False):
+    """Prior sample of every pose, in place: drop-in for ``utils/sampling.py:16-58`` (called by inference.py:237 right before
+    ``sampling``).  Same arguments, same random streams in the same order - numpy's global generator for the torsion angles
+    (all poses first, :33-40) and, through scipy's ``Rotation.random``, for the rotations; Python's ``random`` / torch's
+    global generator for the translation (:45-57) - so a seeded run reproduces the reference's poses bit for bit.
+    Host arithmetic like the reference's (a few hundred flops per pose); what changes is that the poses may be the
+    light-weight ``inputs.pose_copies`` of a device-resident complex: receptor statistics are then taken on the device once
+    and only three floats come back."""
+    import random as _random
+    from scipy.spatial.transform import Rotation as R
+    rec0 = data_list[0]['receptor']
+    lig_dev = data_list[0]['ligand'].pos.device
+    center_pocket = rec0.pos.mean(dim=0).to(lig_dev)
+    if pocket_knowledge:
+        cpx = data_list[0]
+        ref_lig = torch.from_numpy(cpx['ligand'].orig_pos[0]).float() - cpx.original_center.cpu()
+        d = torch.cdist(rec0.pos.cpu(), ref_lig)
+        label = torch.any(d < pocket_cutoff, dim=1)
+        if torch.any(label):
+            center_pocket = rec0.pos.cpu()[label].mean(dim=0)
+        else:
+            print("No pocket residue below minimum distance ", pocket_cutoff, "taking closest at", torch.min(d))
+            center_pocket = rec0.pos.cpu()[torch.argmin(torch.min(d, dim=1)[0])]
+    if not no_torsion:
+        for g in data_list:
+            lig = g['ligand']
+            mask = lig.mask_rotate[0] if isinstance(lig.mask_rotate, list) else lig.mask_rotate
+            updates = np.random.uniform(low=-np.pi, high=np.pi, size=int(lig.edge_mask.sum()))
+            bonds = g['ligand', 'ligand'].edge_index.T[lig.edge_mask].cpu().numpy()
+            pos = lig.pos.cpu().numpy().copy()
+            for k, (u, v) in enumerate(bonds):              # utils/torsion.py:48-72: fp64 rotation, fp32 coordinates
+                if updates[k] == 0:
+                    continue
+                axis = pos[u] - pos[v]
+                rot = R.from_rotvec(axis * updates[k] / np.linalg.norm(axis)).as_matrix()
+                pos[mask[k]] = (pos[mask[k]] - pos[v]) @ rot.T + pos[v]
+            lig.pos = torch.from_numpy(pos.astype(np.float32))
+    rec_sq = None
+    for g in data_list:
+        lig = g['ligand']
+        centre = torch.mean(lig.pos, dim=0, keepdim=True)
+        rot = torch.from_numpy(R.random().as_matrix()).float()
+        lig.pos = (lig.pos - centre) @ rot.T + center_pocket
+        if not no_random:
+            rpos = g['receptor'].pos
+            if choose_residue:
+                idx = _random.randint(0, len(rpos) - 1)
+                tr_update = torch.normal(mean=rpos[idx:idx + 1].cpu(), std=0.01)
+            elif initial_noise_std_proportion >= 0.0:
+                if rec_sq is None or g['receptor'] is not rec0:
+                    rec_sq = torch.sqrt(torch.mean(torch.sum(rpos ** 2, dim=1))).cpu()
+                tr_update = torch.normal(mean=0, std=rec_sq * initial_noise_std_proportion / 1.73, size=(1, 3))   # fp32 product
+            else:
+                tr_update = torch.normal(mean=0, std=-initial_noise_std_proportion * tr_sigma_max, size=(1, 3))
+            lig.pos = lig.pos + tr_update
+
+
 def is_iterable(arr):
     try:
         iter(arr)
