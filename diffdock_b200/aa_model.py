@@ -11,8 +11,11 @@ Two reference behaviours are reproduced on purpose: the reversed groups (residue
 the FORWARD direction's spherical harmonics (:405-406; the coarse-grained model evaluates Y(-v) instead, cg_model.py:556-557),
 and ligand-atom distances go through the ligand distance expansion (:613) into an MLP sized for the cross expansion (:108).
 
-CUDA only, inference only, score mode only.  No CPU fallback.  Neighbour-list sizes are read back to the host (the
-coarse-grained model's sync-free / CUDA-graph path is not wired for the nine-group graph)."""
+CUDA only, inference only, score mode only.  No CPU fallback.  Like the coarse-grained model the forward has a sync-free
+form (``_forward_sync_free``: every per-step neighbour list in a capacity buffer with its live count on the device, the three
+reversed groups as permutations of the forward lists, sigma terms of the four static groups added inside the kernel), so the
+sampler captures the all-atom step in a CUDA graph too; ``_forward_host_sized`` reads the neighbour-list sizes back and is
+used for shapes outside the fused kernel or more than 10000 residues / atoms per complex."""
 from __future__ import annotations
 
 import torch
@@ -84,7 +87,18 @@ class AAModel(CGModel):
                                           for i in range(num_prot_emb_layers, num_prot_emb_layers + num_conv_layers)])
 
     def sync_free_capable(self):
-        return False
+        """As CGModel.sync_free_capable; additionally every edge type must have its own radial MLP (the merged single-group
+        form concatenates edge lists, which needs their sizes on the host)."""
+        if self._sync_free is None:
+            import os
+            ok = os.environ.get('DDB200_SYNC_FREE', '1') != '0' and self.embed_also_ligand and self.differentiate_convolutions
+            for layer in list(self.conv_layers) + list(self.lig_emb_layers):
+                ok = ok and layer.fused_capable(self.ns, self.ns)
+            self._sync_free = bool(ok)
+        return self._sync_free
+
+    def _static(self, data):             # hook of sampling.GraphedSteps: the per-batch constants, outside the capture
+        return self._static_aa(data)
 
     # ---------------------------------------------------------------------------------------------------------
     @staticmethod
@@ -141,6 +155,16 @@ class AAModel(CGModel):
         c['bonds'], c['n_bonds'] = bonds, int(bonds.shape[1])
         c['bond_batch'] = lig.batch[bonds[0]] if bonds.shape[1] else None
         c['bond_lig_batch'] = c['bond_batch']
+        # constants of the sync-free forward: CGModel's (ligand / residue counts, bond CSR, capacities) + the atom side
+        c['rr_tgt_batch'] = rec.batch[rr_ei[0]]
+        self._static_sync_free(data, c)
+        i32 = lambda t: t.to(torch.int32).contiguous()
+        atom_cnt = c['atom_ptr'][1:] - c['atom_ptr'][:-1]
+        lig_cnt = c['lig_ptr'][1:] - c['lig_ptr'][:-1]
+        c['atom_max'] = int(atom_cnt.max()) if B else 0
+        c['cap_la'] = int((lig_cnt.long() * atom_cnt.long()).sum())      # every ligand atom x every atom of its complex
+        c['atom_batch32'] = i32(atom.batch)
+        c['gid32'] = {k: i32(c[k][4]) for k in ('rr', 'ra', 'aa', 'ar')}
         rr._b200aa = c
         return c
 
@@ -153,9 +177,95 @@ class AAModel(CGModel):
             raise RuntimeError("diffdock_b200.AAModel runs on CUDA tensors only (no CPU fallback): data.to('cuda')")
         if self.no_aminoacid_identities:
             rec.x = rec.x * 0
+        c = self._static_aa(data)
+        if self.sync_free_capable() and c['rec_max'] <= 10000 and c['atom_max'] <= 10000:     # the 10000 caps (:595,:610) not binding
+            return self._forward_sync_free(data, c)
+        return self._forward_host_sized(data, c)
+
+    def _forward_sync_free(self, data, c):
+        """The forward without a device->host read (see CGModel._forward_sync_free): ligand graph, ligand-residue and
+        ligand-atom graphs written into upper-bound buffers with device-side counts; the reversed groups (residue<-ligand,
+        atom<-ligand) are permutations of the forward lists and - as in the reference, models/aa_model.py:405-406 - keep the
+        FORWARD direction's edge vector (vec_sign = +1); the four static groups get their sigma term inside the kernel."""
+        lig, rec, atom = data['ligand'], data['receptor'], data['atom']
+        ns, B = self.ns, data.num_graphs
+        dev = lig.pos.device
+        tr_sigma, rot_sigma, tor_sigma = self.t_to_sigma(*[data.complex_t[k] for k in ('tr', 'rot', 'tor')])
+        n_lig, n_rec = lig.batch.shape[0], rec.batch.shape[0]
+        o_r, o_a = n_lig, n_lig + n_rec
+        pos, rpos, apos = lig.pos.float().contiguous(), rec.pos.float().contiguous(), atom.pos.float().contiguous()
+        scan = lambda cnt: torch.cumsum(cnt, 0, dtype=torch.int32)
+
+        sig = self.rec_sigma_embedding(self.timestep_emb_func(data.complex_t['tr'])).contiguous()
+        rec_node, atom_node = rec.rec_node_attr.clone(), atom.atom_node_attr.clone()
+        rec_node[:, :ns] += sig[rec.batch]
+        atom_node[:, :ns] += sig[atom.batch]
+        lig.node_sigma_emb = self.timestep_emb_func(lig.node_t['tr'])
+
+        # -- ligand graph: bonds + radius graph (models/aa_model.py:538-568 = cg_model.py:467-497) ---------------------------
+        cnt = ops.radius_count(pos, pos, c['lig_ptr'], c['lig_batch32'], r=self.lig_max_radius, max_num_neighbors=33,
+                               exclude_self=True) + c['pre_cnt']
+        incl = scan(cnt)
+        ll_n = incl[-1:]
+        ll_tgt, ll_src, ll_vec, ll_eid, _ = ops.graph_fill(
+            pos, pos, c['lig_ptr'], c['lig_batch32'], (incl - cnt).contiguous(), c['cap_ll'], r=self.lig_max_radius,
+            max_num_neighbors=33, exclude_self=True, pre_ptr=c['pre_ptr'], pre_col=c['pre_col'], want_eid=True, fill_row=0)
+        ll_attr = torch.cat([c['pre_attr'][ll_eid.long()], lig.node_sigma_emb[ll_tgt.long()],
+                             self.lig_distance_expansion(ll_vec.norm(dim=-1))], 1)
+        ll_ea = self.lig_edge_embedding(ll_attr)
+        lig_node = self.lig_node_embedding(torch.cat([lig.x.float(), lig.node_sigma_emb], 1))
+        g_ll = (ll_tgt, ll_src, ll_ea, ll_vec, None, dict(n_edges_dev=ll_n))
+        for layer in self.lig_emb_layers:
+            lig_node = layer.forward_groups(lig_node, [g_ll], gather_scalars=ns)
+
+        def cross(xpos, x_ptr, x_batch32, x_max, cap, r, rpg, col_off, mlp, gs):
+            """ligand <- x (x = residues or atoms) and its reverse as a permutation; joint numbering offsets applied."""
+            cnt = ops.radius_count(xpos, pos, x_ptr, c['lig_batch32'], r=r, r_per_graph=rpg, max_num_neighbors=10000)
+            incl = scan(cnt)
+            n_dev = incl[-1:]
+            slot = torch.empty((n_lig, max(x_max, 1)), dtype=torch.int32, device=dev)
+            # the embedding kernel only touches live edges; its library fallback gathers over the whole buffer and needs
+            # valid (zero) rows beyond the live count
+            in_kernel = (gs.offset.shape[0], ns) in ops.EDGE_EMBED_SHAPES and len(mlp) == 4
+            f_tgt, f_src, f_vec, _, _ = ops.graph_fill(xpos, pos, x_ptr, c['lig_batch32'], (incl - cnt).contiguous(), cap, r=r,
+                                                       r_per_graph=rpg, max_num_neighbors=10000, slot_out=slot,
+                                                       slot_ld=slot.shape[1], col_offset=col_off,
+                                                       fill_row=None if in_kernel else 0)
+            cnt_r = ops.radius_count(pos, xpos, c['lig_ptr'], x_batch32, r=r, r_per_graph=rpg, max_num_neighbors=1 << 30)
+            incl_r = scan(cnt_r)
+            b_tgt, b_src, _, _, b_perm = ops.graph_fill(pos, xpos, c['lig_ptr'], x_batch32, (incl_r - cnt_r).contiguous(), cap,
+                                                        r=r, r_per_graph=rpg, max_num_neighbors=1 << 30, want_vec=False,
+                                                        slot_in=slot, y_ptr=x_ptr, slot_ld=slot.shape[1], want_perm=True,
+                                                        row_offset=col_off)
+            ea = self._cross_edge_embedding(lig.node_sigma_emb, f_vec, f_tgt, n_dev, mlp=mlp, gs=gs)
+            fwd = (f_tgt, f_src, ea, f_vec, None, dict(n_edges_dev=n_dev))
+            rev = (b_tgt, b_src, ea, f_vec, None, dict(n_edges_dev=n_dev, edge_perm=b_perm, vec_sign=1.0))
+            return fwd, rev
+
+        # -- ligand cross graphs (:588-623): residues within the (per-complex) cut-off, atoms within lig_max_radius ---------
+        if self.dynamic_max_cross:
+            rpg, r_cross = (tr_sigma * 3 + 20).reshape(-1).float().contiguous(), 1.0
+        else:
+            rpg, r_cross = None, float(self.cross_max_distance)
+        g_lr, g_rl = cross(rpos, c['rec_ptr'], c['rec_batch32'], c['rec_max'], c['cap_cross'], r_cross, rpg, o_r,
+                           self.lr_edge_embedding, self.cross_distance_expansion)
+        g_la, g_al = cross(apos, c['atom_ptr'], c['atom_batch32'], c['atom_max'], c['cap_la'], float(self.lig_max_radius), None, o_a,
+                           self.la_edge_embedding, self.lig_distance_expansion)
+
+        # -- joint graph [ligand | residues | atoms]: nine groups in the reference's order (:401-417) --------------------
+        node = torch.cat([lig_node, rec_node, atom_node], 0)
+        stat = lambda k: (c[k][0], c[k][1], c[k][2], c[k][3], None, dict(ea_add=sig, ea_add_idx=c['gid32'][k]))
+        groups = [g_ll, g_lr, g_la, stat('rr'), g_rl, stat('ra'), stat('aa'), g_al, stat('ar')]
+        L = len(self.conv_layers)
+        for l, layer in enumerate(self.conv_layers):
+            node = layer.forward_groups(node, groups if l < L - 1 else groups[:3], gather_scalars=ns)
+        return self._heads(data, c, node[:n_lig], tr_sigma, rot_sigma, tor_sigma, sync_free=True)
+
+    def _forward_host_sized(self, data, c):
+        """Forward with exactly-sized neighbour lists (the sizes are read back to the host)."""
+        lig, rec, atom = data['ligand'], data['receptor'], data['atom']
         ns, B = self.ns, data.num_graphs
         tr_sigma, rot_sigma, tor_sigma = self.t_to_sigma(*[data.complex_t[k] for k in ('tr', 'rot', 'tor')])
-        c = self._static_aa(data)
         n_lig, n_rec = lig.pos.shape[0], rec.pos.shape[0]
         o_r, o_a = n_lig, n_lig + n_rec
         N = o_a + atom.pos.shape[0]

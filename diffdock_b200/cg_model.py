@@ -384,7 +384,10 @@ class CGModel(nn.Module):
         incl = scan(cnt)
         lr_n = incl[-1:]
         slot = torch.empty((n_lig, max(c['rec_max'], 1)), dtype=torch.int32, device=dev)
-        smooth = self.smooth_edges
+        # rows beyond the live count must be valid (zero) when library ops gather over the whole buffer: the smooth edge
+        # weight, or the embedding MLP when its shape is outside the edge-embedding kernel's templates
+        smooth = self.smooth_edges or not ((self.cross_distance_expansion.offset.shape[0], ns) in ops.EDGE_EMBED_SHAPES
+                                           and len(self.cross_edge_embedding) == 4)
         lr_tgt, lr_src, lr_vec, _, _ = ops.graph_fill(
             rpos, pos, c['rec_ptr'], c['lig_batch32'], (incl - cnt).contiguous(), cap, r=r_cross, r_per_graph=rpg,
             max_num_neighbors=10000, slot_out=slot, slot_ld=slot.shape[1], col_offset=n_lig, fill_row=0 if smooth else None)
@@ -397,7 +400,7 @@ class CGModel(nn.Module):
             want_perm=True, row_offset=n_lig)
         lr_ea = self._cross_edge_embedding(lig.node_sigma_emb, lr_vec, lr_tgt, lr_n)
         lr_ew = None
-        if smooth:
+        if self.smooth_edges:
             cutoff_d = rpg[lig.batch[lr_tgt.long()]] if rpg is not None else r_cross
             lr_ew = ewt(self.get_edge_weight(lr_vec, cutoff_d))
 
@@ -453,18 +456,20 @@ class CGModel(nn.Module):
         cnt_buf[n_lig:].view(B, n1).add_(cnt0.unsqueeze(0))
         return sum_buf, cnt_buf
 
-    def _cross_edge_embedding(self, node_sigma_emb, vec, row, n_dev):
+    def _cross_edge_embedding(self, node_sigma_emb, vec, row, n_dev, mlp=None, gs=None):
         """cross_edge_embedding(cat[sigma_emb[lig], RBF(d)]) (models/cg_model.py:326,553-554): the sigma half of the first
-        Linear is applied per ligand NODE, the rest per edge in one kernel (ddb200_edge_embed)."""
-        l1, l2 = self.cross_edge_embedding[0], self.cross_edge_embedding[-1]
+        Linear is applied per ligand NODE, the rest per edge in one kernel (ddb200_edge_embed).  ``mlp`` / ``gs``: another
+        embedding MLP / distance expansion of the same form (the all-atom model's ligand-residue and ligand-atom edges)."""
+        mlp = self.cross_edge_embedding if mlp is None else mlp
+        gs = self.cross_distance_expansion if gs is None else gs
+        l1, l2 = mlp[0], mlp[-1]
         S = node_sigma_emb.shape[1]
-        gs = self.cross_distance_expansion
-        if (gs.offset.shape[0], self.ns) in ops.EDGE_EMBED_SHAPES and len(self.cross_edge_embedding) == 4:
+        if (gs.offset.shape[0], self.ns) in ops.EDGE_EMBED_SHAPES and len(mlp) == 4:
             u = torch.addmm(l1.bias, node_sigma_emb, l1.weight[:, :S].t()).contiguous()
             return ops.edge_embed(vec, row, u, l1.weight[:, S:].contiguous(), l2.weight.contiguous(), l2.bias.contiguous(),
                                   gs.offset.contiguous(), float(gs.coeff), n_dev)
         attr = torch.cat([node_sigma_emb[row.long()], gs(vec.norm(dim=-1))], 1)      # library path on the padded buffer
-        return self.cross_edge_embedding(attr)
+        return mlp(attr)
 
     # ---------------------------------------------------------------------------------------------------------
     def _forward_host_sized(self, data, c):

@@ -63,9 +63,42 @@ def test_all_atom_score_model_full_width_matches_oracle(built_lib):
         ref = mo(b)
     bg = collate(copy.deepcopy(poses)).to('cuda:0')
     set_time(bg, None, t, t, t, 2, True, 'cuda:0')
+    assert mp.sync_free_capable()                 # the forward below has no device->host read (capacity buffers)
     got = mp(bg)
     for x, y in zip(got[:3], ref[:3]):
         assert rel_err(x, y) < 1e-4
+    # the host-sized forward (exact neighbour-list sizes read back) gives the same scores
+    mp._sync_free = False
+    bh = collate(copy.deepcopy(poses)).to('cuda:0')
+    set_time(bh, None, t, t, t, 2, True, 'cuda:0')
+    host = mp(bh)
+    for x, y in zip(got[:3], host[:3]):
+        assert rel_err(x, y) < 2e-5
+
+
+def test_all_atom_step_in_a_cuda_graph_matches_the_eager_loop(built_lib):
+    """Full-width all-atom model: sampling() captures the nine-group step in a CUDA graph; same poses as the eager loop."""
+    from argparse import Namespace
+    from diffdock_b200.aa_model import AAModel
+    from diffdock_b200.diffusion_utils import get_t_schedule, get_timestep_embedding, t_to_sigma
+    from diffdock_b200.sampling import sampling
+    from diffdock_b200.synthetic import default_model_args, make_pose_list
+    a = default_model_args(num_conv_layers=2, distance_embed_dim=16, cross_distance_embed_dim=16, sigma_embed_dim=16, all_atoms=True)
+    kw = dict(sigma_embed_dim=16, sh_lmax=2, ns=48, nv=10, num_conv_layers=2, lig_max_radius=a.max_radius,
+              rec_max_radius=a.rec_max_radius, cross_max_distance=a.cross_max_distance, center_max_distance=a.center_max_distance,
+              distance_embed_dim=16, cross_distance_embed_dim=16, dynamic_max_cross=True, lm_embedding_type=None,
+              embed_also_ligand=True)
+    torch.manual_seed(5)
+    m = AAModel(partial(t_to_sigma, args=a), torch.device('cuda:0'), get_timestep_embedding('sinusoidal', 16, a.embedding_scale),
+                **kw).eval().to('cuda:0')
+    assert m.sync_free_capable()
+    poses = make_pose_list(3, n_res=40, n_atoms=12, seed=17, tr_sigma_max=a.tr_sigma_max * 0.5, lm_dim=0, all_atoms=True)
+    sched = get_t_schedule('expbeta', 4)
+    run = lambda graph: torch.stack([d['ligand'].pos for d in sampling(
+        copy.deepcopy(poses), m, 4, sched, sched, sched, 'cuda:0', partial(t_to_sigma, args=a), a, batch_size=3, no_random=True,
+        cuda_graph=graph)[0]]).cpu()
+    eager, graphed = run(False), run(True)
+    assert torch.isfinite(graphed).all() and float((eager - graphed).abs().max()) < 2e-3
 
 
 def test_sampler_runs_the_all_atom_score_model(built_lib):
