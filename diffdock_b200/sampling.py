@@ -179,8 +179,10 @@ _GRAPH_POOLS = {}
 
 
 def _graph_pool(device):
-    """Memory pool shared by the step graphs of one device.  torch releases a graph pool when the last graph captured into it
-    dies, so a one-kernel anchor graph keeps it alive for the life of the process."""
+    """(memory pool, capture stream, warm-up stream) shared by the step graphs of one device.  torch releases a graph pool when
+    the last graph captured into it dies, so a one-kernel anchor graph keeps it alive for the life of the process.  The two
+    streams are persistent as well: the caching allocator keeps one block cache per stream, so a fresh side stream per batch
+    (the usual warm-up recipe) made every batch cudaMalloc its working set again."""
     dev = torch.device(device)
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _GRAPH_POOLS:
@@ -190,8 +192,9 @@ def _graph_pool(device):
         torch.cuda.synchronize(dev)
         with torch.cuda.graph(anchor, pool=pool):
             scratch.add_(1.0)
-        _GRAPH_POOLS[key] = (pool, anchor, scratch)
-    return _GRAPH_POOLS[key][0]
+        _GRAPH_POOLS[key] = (pool, anchor, scratch, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    e = _GRAPH_POOLS[key]
+    return e[0], e[3], e[4]
 
 
 class GraphedSteps:
@@ -255,13 +258,14 @@ class GraphedSteps:
         n_warm = 0 if sig in seen else warmup
         seen.add(sig)
         self.steps_done = 0
+        pool, cap_stream, side = _graph_pool(device)
+        cur = torch.cuda.current_stream(device)
         if n_warm:
-            side = torch.cuda.Stream(device=device)
-            side.wait_stream(torch.cuda.current_stream(device))
+            side.wait_stream(cur)
             with torch.cuda.stream(side):
                 for _ in range(n_warm):
                     one_step()
-            torch.cuda.current_stream(device).wait_stream(side)
+            cur.wait_stream(side)
             try:
                 model._graph_warmed = True
             except Exception:
@@ -269,11 +273,24 @@ class GraphedSteps:
         # One memory pool per device shared by all step graphs of this process: a sampling() call captures a new graph per
         # batch (shapes differ from complex to complex); with a private pool each capture would cudaMalloc its whole
         # footprint again (hundreds of ms for a 1500-residue x 40-pose batch) - the blocks of a finished batch's graph are
-        # reused instead.
+        # reused instead.  The capture is opened with capture_begin / capture_end on a persistent stream rather than with the
+        # torch.cuda.graph context manager, which synchronises the device, runs gc.collect() and empties the allocator cache
+        # on entry: measured on BASELINE config 5 that was 50 ms ... 1.9 s per batch (the collector walks every pose graph
+        # the process holds; the emptied cache is re-allocated by the next batch) against 0.15-0.4 s of replays.
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=_graph_pool(device)):
-            one_step()
-        if pos0 is not None:                    # the capture itself executes nothing; undo the discarded warm-up
+        cap_stream.wait_stream(cur)
+        with torch.cuda.stream(cap_stream):
+            self.graph.capture_begin(pool=pool)
+            try:
+                one_step()
+            finally:
+                self.graph.capture_end()
+        cur.wait_stream(cap_stream)
+        # the capture itself executes nothing.  An eager step that ran before it is either step 0 of this run (same kernels,
+        # same device-side step counter and noise streams as a replay) or is undone.
+        if n_warm == 1 and consume_warmup:
+            self.steps_done = 1
+        elif n_warm:
             self.pos.copy_(pos0)
             self.step.zero_()
 
