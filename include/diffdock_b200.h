@@ -209,7 +209,7 @@ int ddb200_radial_mlp(const float* edge_attr, int64_t ld_ea, int ne, const float
  * of a bipartite graph (the reverse direction reads the same attribute rows in another order with the vector negated,
  * models/cg_model.py:556-557) and let poses share one copy of the static receptor edge attributes; ea_add carries the
  * per-complex sigma-embedding term of models/cg_model.py:298-301 without materialising edge_attr + sigma per step.
- * w1_images / w2_images / tiles / mtab: the plan built by diffdock_b200/fused.py (operand images [hi | lo | hi | bias] with
+ * w1_images / w2_images / tiles / mtab: the plan built by diffdock_b200/fused.py (operand images [hi | lo | bias] with
  * 16-column-aligned sections, N tiles = whole rows of one path block, dense Clebsch-Gordan tables [path][3][3][5] padded to
  * 48 floats).  Supported shapes: (mul_out, 2l_out+1) in {(48,1),(10,3),(16,1),(4,3)}, l_in <= 1, spherical harmonics from
  * edge vectors (sh_lmax <= 2), ne + 2 ns <= 144, hidden <= 144.
