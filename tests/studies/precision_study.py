@@ -10,7 +10,8 @@ all schemes and is not what distinguishes them).
     f16x1       fp16(x).fp16(W)                                               (1 product)
     f16+fp8     fp16(x).fp16(W) + e4m3(x_lo).e4m3(W) + e4m3(x).e4m3(W_lo)     (1 f16-rate + 2 fp8-rate products = 2 units)
                 with the power-of-two scales of diffdock_b200/fused.py
-Prints max|a-b| / max|b| of tr / rot / tor scores versus the plain oracle.  Runs in a minute on CPU; test infrastructure.
+Prints max|a-b| / max|b| of tr / rot / tor scores versus the plain oracle.  Runs in a minute on CPU.  Test infrastructure (it
+evaluates the oracle, so it lives under tests/): python tests/studies/precision_study.py
 """
 import argparse
 import os
@@ -19,7 +20,7 @@ import sys
 import torch
 from torch import nn
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def _e4m3(t):
