@@ -134,3 +134,26 @@ def test_packed_complex_round_trip(tmp_path):
         f.truncate(path.stat().st_size - 100)
     with pytest.raises(ValueError, match='truncated'):
         PackedComplex.load(path, pin=False)
+
+
+def test_pose_copies_take_the_shared_receptor_collate():
+    """The sampler's shared-receptor collate recognises ``pose_copies`` by pointer identity (no tensor comparison) and gives the
+    batch the general collate of deep copies gives."""
+    import copy
+    from diffdock_b200.hetero import collate, collate_shared_receptor
+    from diffdock_b200.inputs import pose_copies
+    from diffdock_b200.synthetic import make_complex
+    g = make_complex(n_res=50, n_atoms=9, seed=7)
+    light = pose_copies(g, 4)
+    deep = [copy.deepcopy(g) for _ in range(4)]
+    for i in range(4):
+        light[i]['ligand'].pos = light[i]['ligand'].pos + float(i)
+        deep[i]['ligand'].pos = deep[i]['ligand'].pos + float(i)
+    a, b = collate_shared_receptor(light, 'cpu'), collate(deep)
+    assert a['receptor']._unique == (50, g['receptor', 'receptor'].edge_index.shape[1], 4)
+    for key in ('ligand', 'receptor'):
+        for attr in ('x', 'pos', 'batch'):
+            assert torch.equal(getattr(a[key], attr), getattr(b[key], attr)), (key, attr)
+    for key in (('ligand', 'ligand'), ('receptor', 'receptor')):
+        assert torch.equal(a[key].edge_index, b[key].edge_index), key
+    assert a.num_graphs == 4
