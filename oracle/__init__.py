@@ -22,6 +22,11 @@ tree gcorso/DiffDock @ b4704d9):
 * ``diffusion``, ``sampling`` - utils/diffusion_utils.py, utils/torsion.py:75-90,
                       utils/geometry.py, utils/sampling.py:69-201, utils/so3.py:89-93,
                       utils/torus.py:79-83.
+* ``inputs``        - the input side: datasets/process_mols.py:161-202,279-301 (receptor / ligand
+                      graph construction incl. torch.cdist's fp32 arithmetic), utils/torsion.py:15-45,
+                      utils/inference_utils.py:229-236, datasets/pdbbind.py:215-230; pinned by
+                      ``tests/golden/ref_inputs.pt`` (the unmodified reference functions run by
+                      ``tests/golden/make_golden_inputs.py``).
 
 Pinning status
 --------------
