@@ -79,6 +79,23 @@ def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, pocket_kn
             lig.pos = lig.pos + tr_update
 
 
+def rank_poses(data_list, confidence, original_center, rmsd_classification_cutoff=None):
+    """The epilogue of a docking run, inference.py:274-283: absolute ligand coordinates of every pose (the graphs are centred
+    on the receptor: + ``original_center``) ordered by decreasing confidence.  ``confidence``: what ``sampling`` returned (None:
+    poses stay in sampling order); a list-valued ``rmsd_classification_cutoff`` (multi-threshold confidence head) ranks by the
+    first output column, as the reference does.  Returns (ligand_pos [N, n_atoms, 3] float array, confidence [N] or None,
+    re_order [N] or None).  ONE device->host copy for all poses instead of one per pose."""
+    pos = torch.stack([g['ligand'].pos for g in data_list])
+    ligand_pos = pos.cpu().numpy() + torch.as_tensor(original_center).cpu().numpy()
+    if confidence is None:
+        return ligand_pos, None, None
+    if isinstance(rmsd_classification_cutoff, list):
+        confidence = confidence[:, 0]
+    confidence = confidence.cpu().numpy()
+    re_order = np.argsort(confidence)[::-1]
+    return ligand_pos[re_order], confidence[re_order], re_order
+
+
 def is_iterable(arr):
     try:
         iter(arr)

@@ -39,3 +39,26 @@ def test_randomize_position_on_shared_receptor_copies():
     for p, want in zip(poses, c['pos_out']):
         assert torch.equal(p['ligand'].pos, want)
     assert not torch.equal(poses[0]['ligand'].pos, poses[1]['ligand'].pos)
+
+
+def test_rank_poses_matches_the_reference_epilogue():
+    """inference.py:274-283 restated on arrays: + original_center, first column of a multi-threshold head, argsort descending."""
+    from diffdock_b200.hetero import HeteroGraph
+    from diffdock_b200.sampling import rank_poses
+    g = torch.Generator().manual_seed(0)
+    poses = []
+    for _ in range(5):
+        h = HeteroGraph()
+        h['ligand'].pos = torch.randn(7, 3, generator=g)
+        poses.append(h)
+    centre = torch.tensor([[10.0, -2.0, 3.5]])
+    conf = torch.randn(5, 2, generator=g)
+    got_pos, got_conf, order = rank_poses(poses, conf, centre, rmsd_classification_cutoff=[2.0, 5.0])
+    want_pos = np.asarray([p['ligand'].pos.cpu().numpy() + centre.cpu().numpy() for p in poses])
+    c = conf[:, 0].cpu().numpy()
+    ro = np.argsort(c)[::-1]
+    assert np.array_equal(order, ro) and np.array_equal(got_conf, c[ro]) and np.array_equal(got_pos, want_pos[ro])
+    p2, c2, o2 = rank_poses(poses, None, centre)
+    assert c2 is None and o2 is None and np.array_equal(p2, want_pos)
+    p3, c3, _ = rank_poses(poses, conf[:, 1], centre, rmsd_classification_cutoff=2.0)
+    assert np.array_equal(c3, np.sort(conf[:, 1].numpy())[::-1])
