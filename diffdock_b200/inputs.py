@@ -21,7 +21,6 @@ No CPU fallback for the device parts: ``contact_graph`` needs the CUDA library a
 """
 from __future__ import annotations
 
-import io
 import json
 import struct
 from typing import Dict, List, Optional, Sequence
