@@ -21,15 +21,18 @@ N_BOND_TYPES = 4          # process_mols.py:57: SINGLE, DOUBLE, TRIPLE, AROMATIC
 
 
 def _fma32(a, b, c):
-    """fp32 fused multiply-add, emulated through fp64 (the product of two fp32 numbers is exact in fp64)."""
-    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+    """fp32 fused multiply-add, emulated in extended precision: the product of two fp32 numbers is exact in 48 bits and the
+    sum with a third fits numpy's longdouble (64-bit significand on x86) in all but astronomically rare alignments, so the
+    single rounding to fp32 is the FMA's (plain fp64 would round twice)."""
+    wide = np.longdouble if np.finfo(np.longdouble).nmant >= 63 else np.float64
+    return (a.astype(wide) * b.astype(wide) + c.astype(wide)).astype(np.float32)
 
 
 def cdist_sq_f32(x):
     """Squared distances as ``torch.cdist(x, x)`` forms them for fp32 ``x`` [N, 3] (process_mols.py:176 calls it on the
     C-alpha coordinates).  More than 25 points -> ATen's ``_euclidean_dist``: ``[-2 x_i, |x_i|^2, 1] . [x_j, 1, |x_j|^2]``
     by an sgemm with K = 5 - one FMA chain in k order - then clamp_min(0); otherwise the direct form sum (a - b)^2.
-    tests/test_inputs_cpu.py checks the matrix-multiply form bit for bit against the installed torch."""
+    tests/test_inputs_cpu.py checks both forms bit for bit against the installed torch."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     n = x.shape[0]
     if n > 25:

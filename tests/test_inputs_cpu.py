@@ -31,6 +31,9 @@ def test_cdist_restatement_is_torch_cdist():
         d, t = cdist_f32(x.numpy()), torch.cdist(x, x).numpy()
         ulp = np.spacing(np.maximum(d, t))
         assert np.all(np.abs(d - t) <= ulp) and np.mean(d == t) > 0.98
+    for n in (2, 7, 25):          # direct form (<= 25 points): torch takes an exact root there, so the distances agree bit for bit
+        x = (torch.randn(n, 3, generator=g) * 20 + 30).float()
+        assert np.array_equal(cdist_f32(x.numpy()), torch.cdist(x, x).numpy()), n
 
 
 @pytest.mark.parametrize('i', range(5))
